@@ -1,0 +1,738 @@
+// lt_device.cuh -- device functions of the particle step (sm_100a).
+//
+// Each function names the reference routine whose RESULT it reproduces
+// (file:line relative to the reference's Model/ directory).  The structure is not
+// the reference's: interpolation weights are computed once per (grid, RK stage)
+// instead of once per value, the three hydro time levels come from one vector
+// load, s-level depths are evaluated on demand instead of being tabulated, and a
+// 4-knot tension spline only solves the interval it is evaluated in.
+#pragma once
+#include <math.h>
+#include "lt_types.h"
+
+#define LT_DEV __device__ __forceinline__
+#define LT_DEVN __device__ __noinline__
+
+#define kF32_1em3 0.001f        // DBLE(0.001)    is a float32 literal widened (LTRANS.f90:901)
+#define kF32_1em6 0.000001f     // DBLE(0.000001) likewise                     (LTRANS.f90:1002)
+
+// ---------------------------------------------------------------- fields ----
+template <class T>
+LT_DEV void load_bcf(const T* base, size_t idx, int sb, int sc, int sf, double& b, double& c, double& f);
+
+LT_DEV double sel4(double a0, double a1, double a2, double a3, int s)
+{
+    double lo = (s & 1) ? a1 : a0, hi = (s & 1) ? a3 : a2;
+    return (s & 2) ? hi : lo;
+}
+template <>
+LT_DEV void load_bcf<float>(const float* base, size_t idx, int sb, int sc, int sf, double& b, double& c, double& f)
+{
+    float4 q = __ldg(reinterpret_cast<const float4*>(base) + idx);
+    double a0 = (double)q.x, a1 = (double)q.y, a2 = (double)q.z, a3 = (double)q.w;
+    b = sel4(a0, a1, a2, a3, sb); c = sel4(a0, a1, a2, a3, sc); f = sel4(a0, a1, a2, a3, sf);
+}
+template <>
+LT_DEV void load_bcf<double>(const double* base, size_t idx, int sb, int sc, int sf, double& b, double& c, double& f)
+{
+    const double2* p = reinterpret_cast<const double2*>(base) + 2 * idx;
+    double2 lo = __ldg(p), hi = __ldg(p + 1);
+    b = sel4(lo.x, lo.y, hi.x, hi.y, sb); c = sel4(lo.x, lo.y, hi.x, hi.y, sc); f = sel4(lo.x, lo.y, hi.x, hi.y, sf);
+}
+
+// ------------------------------------------------------------- polintd ------
+// interpolation_module.f90:70-107 (n = 3), same operation order.
+LT_DEV double polintd(const double* xa, double y1, double y2, double y3, double x)
+{
+    int ns = 1; double dif = fabs(x - xa[0]);
+    double d2 = fabs(x - xa[1]); if (d2 < dif) { ns = 2; dif = d2; }
+    double d3 = fabs(x - xa[2]); if (d3 < dif) { ns = 3; dif = d3; }
+    double c = (xa[1] - x) * ((y3 - y2) / (xa[1] - xa[2]));
+    c = c - (xa[1] - x) * ((y2 - y1) / (xa[0] - xa[1]));
+    c = c / (xa[0] - xa[2]);
+    double a, b;
+    if (ns == 3) { a = (y3 - y2) / (xa[1] - xa[2]); b = xa[2] - x; }
+    else         { a = (y2 - y1) / (xa[0] - xa[1]); b = xa[0] - x; }
+    double yn = ns == 1 ? y1 : ns == 2 ? y2 : y3;
+    double xn = ns == 1 ? xa[0] : ns == 2 ? xa[1] : xa[2];
+    return yn + (xn - x) * a + b * c;
+}
+// time polynomial with the p == 1 triplet (b,b,c) of LTRANS.f90:1534-1544
+LT_DEV double time_poly(const LtDev& D, double vb, double vc, double vf, double x)
+{
+    return D.p == 1 ? polintd(D.ex, vb, vb, vc, x) : polintd(D.ex, vb, vc, vf, x);
+}
+
+// ------------------------------------------------------------- gridcell -----
+// gridcell_module.f90:26-257, single element.  q = x0..x3,y0..y3.
+LT_DEVN bool gridcell(const double* __restrict__ q, double X, double Y)
+{
+    double x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3], y0 = q[4], y1 = q[5], y2 = q[6], y3 = q[7];
+    if ((Y < y0 && Y < y1 && Y < y2 && Y < y3) || (Y > y0 && Y > y1 && Y > y2 && Y > y3)) return false;
+    if ((X < x0 && X < x1 && X < x2 && X < x3) || (X > x0 && X > x1 && X > x2 && X > x3)) return false;
+    if ((X == x0 && Y == y0) || (X == x1 && Y == y1) || (X == x2 && Y == y2) || (X == x3 && Y == y3)) return true;
+    const double ex[4] = {x0, x1, x2, x3}, ey[4] = {y0, y1, y2, y3};
+    // horizontal pairs in the reference's order 12,13,14,23,24,34
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b)
+            if (ey[a] == ey[b] && Y == ey[a])
+                return (ex[a] > ex[b] && X > ex[b] && X < ex[a]) || (ex[b] > ex[a] && X > ex[a] && X < ex[b]);
+    if (Y == y0 || Y == y1 || Y == y2 || Y == y3) {
+        double hi = fmax(fmax(y0, y1), fmax(y2, y3)), lo = fmin(fmin(y0, y1), fmin(y2, y3));
+        if (Y == hi || Y == lo) return false;
+    }
+    int total = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        double bx1 = ex[p], by1 = ey[p], bx2 = ex[(p + 1) & 3], by2 = ey[(p + 1) & 3];
+        if (X <= bx1 || X <= bx2) {
+            if ((by1 > by2 && Y >= by2 && Y <= by1) || (by2 > by1 && Y >= by1 && Y <= by2)) {
+                if (bx1 == bx2) {
+                    if (X == bx1) return true;
+                    if (Y != by2) total++;
+                } else {
+                    double slope = (by1 - by2) / (bx1 - bx2);
+                    double xi = (Y - by1 + (slope * bx1)) / slope;
+                    if (xi == X) return true;
+                    if (xi > X && Y != by2) total++;
+                }
+            }
+        }
+    }
+    return (total & 1) != 0;
+}
+
+// setEle (hydro:1414-1532), neighbour-search form.  Returns false for "jumped over
+// an element" (a 0 entry reached, ledger 17).  If all 10 entries are non-zero and none
+// matches, the reference raises nothing and keeps the old element (hydro:1464-1476).
+LT_DEV bool find_element(const LtGridTab& G, double X, double Y, int& ele)
+{
+    const int* row = G.adj + (size_t)(ele - 1) * 10;
+    for (int i = 0; i < 10; ++i) {
+        int check = __ldg(row + i);
+        if (check == 0) return false;
+        if (gridcell(G.ele + (size_t)(check - 1) * 8, X, Y)) { ele = check; return true; }
+    }
+    return true;
+}
+
+// ------------------------------------------------- interpolation weights ----
+struct Wt { int mode; double t, u; };   // 1,2: triangles (hydro:1706-1714); 3: IDW; 4..7: on node 1..4
+
+// setInterp (hydro:1680-1740) when `setinterp_quirk` (an on-node point outside both
+// triangles keeps tOK = 2), interp (hydro:2533-2565) otherwise.
+LT_DEV Wt make_weights(const double* __restrict__ q, double xp, double yp, bool setinterp_quirk)
+{
+    double x1 = q[0], x2 = q[1], x3 = q[2], x4 = q[3], y1 = q[4], y2 = q[5], y3 = q[6], y4 = q[7];
+    Wt w;
+    w.t = ((xp - x1) * (y3 - y1) + (y1 - yp) * (x3 - x1)) / ((x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1));
+    w.u = ((xp - x1) * (y2 - y1) + (y1 - yp) * (x2 - x1)) / ((x3 - x1) * (y2 - y1) - (y3 - y1) * (x2 - x1));
+    w.mode = 1;
+    if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
+        w.t = ((xp - x3) * (y1 - y3) + (y3 - yp) * (x1 - x3)) / ((x4 - x3) * (y1 - y3) - (y4 - y3) * (x1 - x3));
+        w.u = ((xp - x3) * (y4 - y3) + (y3 - yp) * (x4 - x3)) / ((x1 - x3) * (y4 - y3) - (y1 - y3) * (x4 - x3));
+        w.mode = 2;
+        if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
+            bool n1 = xp == x1 && yp == y1, n2 = xp == x2 && yp == y2, n3 = xp == x3 && yp == y3, n4 = xp == x4 && yp == y4;
+            if (n1 || n2 || n3 || n4) {
+                if (!setinterp_quirk) w.mode = n4 ? 7 : n3 ? 6 : n2 ? 5 : 4;
+            } else w.mode = 3;
+        }
+    }
+    return w;
+}
+LT_DEV double combine(const Wt& w, const double* __restrict__ q, double xp, double yp,
+                      double v1, double v2, double v3, double v4)
+{
+    if (w.mode == 1) return v1 + (v2 - v1) * w.t + (v3 - v1) * w.u;
+    if (w.mode == 2) return v3 + (v4 - v3) * w.t + (v1 - v3) * w.u;
+    if (w.mode == 3) {   // inverse distance (rare: extrapolating RK sub-stage points)
+        double D1 = 1. / sqrt((q[0] - xp) * (q[0] - xp) + (q[4] - yp) * (q[4] - yp));
+        double D2 = 1. / sqrt((q[1] - xp) * (q[1] - xp) + (q[5] - yp) * (q[5] - yp));
+        double D3 = 1. / sqrt((q[2] - xp) * (q[2] - xp) + (q[6] - yp) * (q[6] - yp));
+        double D4 = 1. / sqrt((q[3] - xp) * (q[3] - xp) + (q[7] - yp) * (q[7] - yp));
+        double TD = D1 + D2 + D3 + D4;
+        return (D1 / TD) * v1 + (D2 / TD) * v2 + (D3 / TD) * v3 + (D4 / TD) * v4;
+    }
+    return w.mode == 4 ? v1 : w.mode == 5 ? v2 : w.mode == 6 ? v3 : v4;
+}
+
+// free-slip corner substitution (hydro:1936-1994, 2330-2519), incl. ledger 16
+LT_DEVN void freeslip(double* v, const int* m, int one_land_sum, const int* md)
+{
+    int sum = m[0] + m[1] + m[2] + m[3];
+    if (sum >= 4) return;
+    if (sum == one_land_sum) {
+        if (m[0] == 0) v[0] = 0.5 * (v[1] + v[3]);
+        else if (m[1] == 0) v[1] = 0.5 * (v[0] + v[2]);
+        else if (m[2] == 0) v[2] = 0.5 * (v[1] + v[3]);
+        else if (m[3] == 0) v[3] = 0.5 * (v[0] + v[2]);
+    } else if (sum == 2) {
+        if (m[0] == 0 && m[1] == 0) { v[0] = v[3]; v[1] = v[2]; }
+        else if (m[1] == 0 && m[2] == 0) { v[1] = v[0]; v[2] = v[3]; }
+        else if (m[2] == 0 && m[3] == 0) { v[2] = v[1]; v[3] = v[0]; }
+        else if (m[3] == 0 && m[0] == 0) { v[3] = v[2]; v[0] = v[1]; }
+        else if (md[0] == 0 && md[2] == 0) { v[0] = v[3]; v[2] = v[1]; }
+        else if (md[3] == 0 && md[1] == 0) { v[3] = v[0]; v[1] = v[2]; }
+    } else if (sum == 1) {
+        if (m[0] == 1) { v[1] = v[0]; v[2] = v[0]; v[3] = v[0]; }
+        else if (m[1] == 1) { v[0] = v[1]; v[2] = v[1]; v[3] = v[1]; }
+        else if (m[2] == 1) { v[0] = v[2]; v[1] = v[2]; v[3] = v[2]; }
+        else if (m[3] == 1) { v[0] = v[3]; v[1] = v[3]; v[2] = v[3]; }
+    }
+}
+
+// which grid a stencil sits on
+enum { G_RHO = 0, G_U = 1, G_V = 2 };
+struct Stencil {            // element corner nodes + coordinates + weights at one point
+    int4 nd; const double* q; Wt w; double xp, yp;
+};
+
+// value of one (field, level) at the three hydro times: the 4-corner gather of
+// getInterp (hydro:1743-2005) / interp (hydro:2008-2569) with precomputed weights.
+template <class T>
+LT_DEV void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
+                       double& rb, double& rc, double& rf)
+{
+    double b[4], c[4], f[4];
+    load_bcf<T>(fld, (size_t)s.nd.x * L + lev0, D.sb, D.sc, D.sf, b[0], c[0], f[0]);
+    load_bcf<T>(fld, (size_t)s.nd.y * L + lev0, D.sb, D.sc, D.sf, b[1], c[1], f[1]);
+    load_bcf<T>(fld, (size_t)s.nd.z * L + lev0, D.sb, D.sc, D.sf, b[2], c[2], f[2]);
+    load_bcf<T>(fld, (size_t)s.nd.w * L + lev0, D.sb, D.sc, D.sf, b[3], c[3], f[3]);
+    if (D.P.FreeSlip) {
+        const uint8_t* mk = grid == G_RHO ? D.R.mask : grid == G_U ? D.U.mask : D.V.mask;
+        int m[4] = { mk[s.nd.x], mk[s.nd.y], mk[s.nd.z], mk[s.nd.w] }, md[4];
+        md[0] = m[0]; md[1] = m[1]; md[2] = m[2]; md[3] = m[3];
+        if (grid == G_V) {   // v_mask(unode*) in the diagonal test (hydro:2500-2503); out of range -> water
+            int nv = D.V.nodes;
+            md[0] = und.x < nv ? D.V.mask[und.x] : 1; md[1] = und.y < nv ? D.V.mask[und.y] : 1;
+            md[2] = und.z < nv ? D.V.mask[und.z] : 1; md[3] = und.w < nv ? D.V.mask[und.w] : 1;
+        }
+        int one = grid == G_U ? 1 : 3;                       // hydro:2408
+        freeslip(b, m, one, md); freeslip(c, m, one, md); freeslip(f, m, one, md);
+    }
+    rb = combine(s.w, s.q, s.xp, s.yp, b[0], b[1], b[2], b[3]);
+    rc = combine(s.w, s.q, s.xp, s.yp, c[0], c[1], c[2], c[3]);
+    rf = combine(s.w, s.q, s.xp, s.yp, f[0], f[1], f[2], f[3]);
+}
+
+LT_DEV double gather_static(const LtDev& D, const double* arr, const Stencil& s)
+{
+    double v[4] = { __ldg(arr + s.nd.x), __ldg(arr + s.nd.y), __ldg(arr + s.nd.z), __ldg(arr + s.nd.w) };
+    if (D.P.FreeSlip) {
+        int m[4] = { D.R.mask[s.nd.x], D.R.mask[s.nd.y], D.R.mask[s.nd.z], D.R.mask[s.nd.w] };
+        freeslip(v, m, 3, m);
+    }
+    return combine(s.w, s.q, s.xp, s.yp, v[0], v[1], v[2], v[3]);
+}
+
+// --------------------------------------------------------------- s-levels ---
+// getSlevel / getWlevel (hydro:2691-2777); depth < 0, hc widened from REAL(4).
+LT_DEV double zlevel(const LtDev& D, double zeta, double depth, double sc, double cs)
+{
+    double hc = (double)D.P.hc, h = -1.0 * depth, S;
+    if (D.P.Vtransform == 1) { S = hc * sc + (h - hc) * cs; return S + zeta * (1.0 + S / h); }
+    if (D.P.Vtransform == 2) { S = (hc * sc + h * cs) / (hc + h); return zeta + (zeta + h) * S; }
+    return zeta * (1.0 + sc) + hc * sc + (h - hc) * cs;
+}
+struct Column { double zb, zc, zf, depth; };     // zeta at the 3 times + (negative) depth
+LT_DEV double zr(const LtDev& D, const Column& c, double zeta, int k) { return zlevel(D, zeta, c.depth, D.SC[k], D.CS[k]); }
+LT_DEV double zw(const LtDev& D, const Column& c, double zeta, int k) { return zlevel(D, zeta, c.depth, D.SCW[k], D.CSW[k]); }
+
+// first i in [3, n-2] (1-based) with Z below level i at any of the 3 times, else n-1;
+// returns i-2 (LTRANS.f90:1451-1467).  Levels increase with i, so the linear scan of
+// the reference is a lower_bound: bisect.
+template <bool W>
+LT_DEV int level_window(const LtDev& D, const Column& c, double Z, int n)
+{
+    int lo = 3, hi = n - 1;          // answer i in [3, n-1]
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;    // test level mid (1-based) -> index mid-1
+        double sc = W ? D.SCW[mid - 1] : D.SC[mid - 1], cs = W ? D.CSW[mid - 1] : D.CS[mid - 1];
+        bool below = Z < zlevel(D, c.zb, c.depth, sc, cs) || Z < zlevel(D, c.zc, c.depth, sc, cs) ||
+                     Z < zlevel(D, c.zf, c.depth, sc, cs);
+        if (below) hi = mid; else lo = mid + 1;
+    }
+    return lo - 2;
+}
+
+// ---------------------------------------------------------------- TSPACK ----
+// SNHCSH tension_module.f90:784-850
+LT_DEV void snhcsh(double X, double& SINHM, double& COSHM, double& COSHMM)
+{
+    const double P1 = -3.51754964808151394800e5, P2 = -1.15614435765005216044e4,
+                 P3 = -1.63725857525983828727e2, P4 = -7.89474443963537015605e-1,
+                 Q1 = -2.11052978884890840399e6, Q2 = 3.61578279834431989373e4,
+                 Q3 = -2.77711081420602794433e2, Q4 = 1.0;
+    double AX = fabs(X), XS = AX * AX;
+    if (AX <= .5) {
+        double XC = X * XS;
+        double P = ((P4 * XS + P3) * XS + P2) * XS + P1;
+        double Q = ((Q4 * XS + Q3) * XS + Q2) * XS + Q1;
+        SINHM = XC * (P / Q);
+        double XSD4 = .25 * XS, XSD2 = XSD4 + XSD4;
+        P = ((P4 * XSD4 + P3) * XSD4 + P2) * XSD4 + P1;
+        Q = ((Q4 * XSD4 + Q3) * XSD4 + Q2) * XSD4 + Q1;
+        double F = XSD4 * (P / Q);
+        COSHMM = XSD2 * F * (F + 2.0);
+        COSHM = COSHMM + XSD2;
+    } else {
+        double EXPX = exp(AX);
+        SINHM = -(((1.0 / EXPX + AX) + AX) - EXPX) / 2.0;
+        if (X < 0.0) SINHM = -SINHM;
+        COSHM = ((1.0 / EXPX - 2.0) + EXPX) / 2.0;
+        COSHMM = COSHM - XS / 2.0;
+    }
+}
+
+// SIGS (tension_module.f90:314-782) for ONE interval: minimum tension factor on
+// [x_i, x_i+1] given the end slopes.  Intervals are independent in SIGS (TOL = 0,
+// SIGMA zeroed on entry), so solving only the interval that is evaluated gives the
+// value the reference's full sweep stores for it.  err = 1 <=> NIT > 10000 (SigErr).
+#define LT_RTOL (200.0 * 1.1102230246251565e-16)      /* 200 * 2^-53, the :433-439 loop */
+LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double S2, int& err)
+{
+    const double SBIG = 85.0, RTOL = LT_RTOL, FTOL = 0.0;
+    double S = (Y2 - Y1) / DX;
+    double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
+    if ((D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0)) return SBIG;
+    double SIG = 0.0;
+    if (D1D2 >= 0.0) {
+        if (D1D2 == 0.0) return 0.0;
+        double T = fmax(D1 / D2, D2 / D1);
+        if (T <= 2.0) return 0.0;
+        double TP1 = T + 1.0;
+        SIG = sqrt(10.0 * T - 20.0);
+        int NIT = 0;
+        for (;;) {
+            double T1, FP;
+            if (SIG <= .5) {
+                double SINHM, COSHM, COSHMM;
+                snhcsh(SIG, SINHM, COSHM, COSHMM);
+                T1 = COSHM / SINHM;
+                FP = T1 + SIG * (SIG / SINHM - T1 * T1 + 1.0);
+            } else {
+                double EMS = exp(-SIG);
+                double SSM = 1.0 - EMS * (EMS + SIG + SIG);
+                T1 = (1.0 - EMS) * (1.0 - EMS) / SSM;
+                FP = T1 + SIG * (2.0 * SIG * EMS / SSM - T1 * T1 + 1.0);
+            }
+            double F = SIG * T1 - TP1;
+            if (++NIT > 10000) { err = 1; return 0.0; }
+            if (FP <= 0.0) break;
+            double DSIG = -F / FP;
+            if (fabs(DSIG) <= RTOL * SIG || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
+            SIG = SIG + DSIG;
+        }
+        return fmin(SIG, SBIG);
+    }
+    // monotonicity :638-760
+    if (S1 * S < 0.0 || S2 * S < 0.0) return 0.0;
+    double T0 = 3.0 * S - S1 - S2;
+    double D0 = T0 * T0 - S1 * S2;
+    if (D0 <= 0.0 || S * T0 >= 0.0) return 0.0;
+    double SGN = copysign(1.0, S);
+    SIG = SBIG;
+    double FMAX = SGN * (SIG * S - S1 - S2) / (SIG - 2.0);
+    if (FMAX <= 0.0) return SBIG;
+    double STOL = RTOL * SIG, F = FMAX, F0 = SGN * D0 / (3.0 * (D1 - D2)), FNEG = F0;
+    double DSIG = SIG, DMAX = SIG, D1PD2 = D1 + D2, A = 0.0, E = 0.0;
+    bool CONT = true;                                  // ledger 18
+    int NIT = 0;
+    for (;;) {
+        DSIG = -F * DSIG / (F - F0);
+        if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { err = 1; return 0.0; } continue; }
+        if (fabs(DSIG) < STOL / 2.0) DSIG = -copysign(STOL / 2.0, DMAX);
+        SIG = SIG + DSIG;
+        F0 = F;
+        double C1, C2;
+        if (SIG <= .5) {
+            double SINHM, COSHM, COSHMM;
+            snhcsh(SIG, SINHM, COSHM, COSHMM);
+            C1 = SIG * COSHM * D2 - SINHM * D1PD2;
+            C2 = SIG * (SINHM + SIG) * D2 - COSHM * D1PD2;
+            A = C2 - C1;
+            E = SIG * SINHM - COSHMM - COSHMM;
+        } else {
+            double EMS = exp(-SIG), EMS2 = EMS + EMS, TM = 1.0 - EMS;
+            double SSINH = TM * (1.0 + EMS), SSM = SSINH - SIG * EMS2, SCM = TM * TM;
+            C1 = SIG * SCM * D2 - SSM * D1PD2;
+            C2 = SIG * SSINH * D2 - SCM * D1PD2;
+            F = FMAX;
+            CONT = true;
+            if (C1 * (SIG * SCM * D1 - SSM * D1PD2) >= 0.0) CONT = false;
+            if (CONT) A = EMS2 * (SIG * TM * D2 + (TM - SIG) * D1PD2);
+            if (A * (C2 + C1) < 0.0) CONT = false;
+            if (CONT) E = SIG * SSINH - SCM - SCM;
+        }
+        if (CONT) F = (SGN * (E * S2 - C2) + sqrt(A * (C2 + C1))) / E;
+        if (++NIT > 100000) { err = 1; return 0.0; }
+        STOL = RTOL * SIG;
+        if (fabs(DMAX) <= STOL || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
+        DMAX = DMAX + DSIG;
+        if (F0 * F > 0.0 && fabs(F) >= fabs(F0)) { DSIG = DMAX; F0 = FNEG; continue; }
+        if (F0 * F <= 0.0) {
+            double T1 = DMAX, T2 = FNEG;
+            DMAX = DSIG; FNEG = F0;
+            if (fabs(DSIG) > fabs(T1) && fabs(F) < fabs(T2)) { DSIG = T1; F0 = T2; }
+        }
+    }
+    return fmin(SIG, SBIG);
+}
+
+// HVAL on one interval (tension_module.f90:1043-1117)
+LT_DEVN double hval_interval(double T, double X1, double X2, double Y1, double Y2, double YP1, double YP2, double SIGMA)
+{
+    const double SBIG = 85.0;
+    double DX = X2 - X1, U = T - X1, B2 = U / DX, B1 = 1.0 - B2, S1 = YP1;
+    double S = (Y2 - Y1) / DX, D1 = S - S1, D2 = YP2 - S, SIG = fabs(SIGMA);
+    if (SIG < 1.e-9) return Y1 + U * (S1 + B2 * (D1 + B1 * (D1 - D2)));
+    if (SIG <= .5) {
+        double SB2 = SIG * B2, SM, CM, CMM, SM2, CM2, DUMMY;
+        snhcsh(SIG, SM, CM, CMM); snhcsh(SB2, SM2, CM2, DUMMY);
+        double E = SIG * SM - CMM - CMM;
+        return Y1 + S1 * U + DX * ((CM * SM2 - SM * CM2) * (D1 + D2) + SIG * (CM * CM2 - (SM + SIG) * SM2) * D1) / (SIG * E);
+    }
+    double SB1 = SIG * B1, SB2 = SIG - SB1;
+    if (-SB1 > SBIG || -SB2 > SBIG) return Y1 + S * U;
+    double E1 = exp(-SB1), E2 = exp(-SB2), EMS = E1 * E2, TM = 1.0 - EMS, TS = TM * TM, TP = 1.0 + EMS;
+    double E = TM * (SIG * TP - TM - TM);
+    return Y1 + S * U + DX * (TM * (TP - E1 - E2) * (D1 + D2) +
+           SIG * ((E2 + EMS * (E1 - 2.0) - B1 * TS) * D1 + (E1 + EMS * (E2 - 2.0) - B2 * TS) * D2)) / (SIG * E);
+}
+// HPVAL on one interval (tension_module.f90:1190-1249)
+LT_DEVN double hpval_interval(double T, double X1, double X2, double Y1, double Y2, double YP1, double YP2, double SIGMA)
+{
+    const double SBIG = 85.0;
+    double DX = X2 - X1, B1 = (X2 - T) / DX, B2 = 1.0 - B1, S1 = YP1;
+    double S = (Y2 - Y1) / DX, D1 = S - S1, D2 = YP2 - S, SIG = fabs(SIGMA);
+    if (SIG < 1.e-9) return S1 + B2 * (D1 + D2 - 3.0 * B1 * (D2 - D1));
+    if (SIG <= .5) {
+        double SB2 = SIG * B2, SM, CM, CMM, SM2, CM2, DUMMY;
+        snhcsh(SIG, SM, CM, CMM); snhcsh(SB2, SM2, CM2, DUMMY);
+        double SINH2 = SM2 + SB2, E = SIG * SM - CMM - CMM;
+        return S1 + ((CM * CM2 - SM * SINH2) * (D1 + D2) + SIG * (CM * SINH2 - (SM + SIG) * CM2) * D1) / E;
+    }
+    double SB1 = SIG * B1, SB2 = SIG - SB1;
+    if (-SB1 > SBIG || -SB2 > SBIG) return S;
+    double E1 = exp(-SB1), E2 = exp(-SB2), EMS = E1 * E2, TM = 1.0 - EMS;
+    double E = TM * (SIG * (1.0 + EMS) - TM - TM);
+    return S + (TM * ((E2 - E1) * (D1 + D2) + TM * (D1 - D2)) + SIG * ((E1 * EMS - E2) * D1 + (E1 - E2 * EMS) * D2)) / E;
+}
+
+// YPC1 interior / end formulas (tension_module.f90:852-978)
+LT_DEV double ypc1_end(double SI, double T) { return SI >= 0.0 ? fmin(fmax(0.0, T), 3.0 * SI) : fmax(fmin(0.0, T), 3.0 * SI); }
+LT_DEV double ypc1_mid(double DXIM1, double DXI, double SIM1, double SI)
+{
+    double T = (DXIM1 * SI + DXI * SIM1) / (DXIM1 + DXI);
+    double ASIM1 = fabs(SIM1), ASI = fabs(SI);
+    double SGN = copysign(1.0, SI);
+    if (ASIM1 > ASI) SGN = copysign(1.0, SIM1);
+    return SGN > 0.0 ? fmin(fmax(0.0, T), 3.0 * fmin(ASIM1, ASI)) : fmax(fmin(0.0, T), -3.0 * fmin(ASIM1, ASI));
+}
+
+// TSPSI(N=4) + HVAL, or the linint fallback: the water-column profile value of
+// WCTS_ITPI (hydro:2619-2644) at T.
+LT_DEVN double spline4_eval(const double* __restrict__ X, const double* __restrict__ Y, double T)
+{
+    double dx1 = X[1] - X[0], dx2 = X[2] - X[1], dx3 = X[3] - X[2];
+    double s1 = (Y[1] - Y[0]) / dx1, s2 = (Y[2] - Y[1]) / dx2, s3 = (Y[3] - Y[2]) / dx3;
+    double YP[4];
+    YP[0] = ypc1_end(s1, s1 + dx1 * (s1 - s2) / (dx1 + dx2));
+    YP[1] = ypc1_mid(dx1, dx2, s1, s2);
+    YP[2] = ypc1_mid(dx2, dx3, s2, s3);
+    YP[3] = ypc1_end(s3, s3 + dx3 * (s3 - s2) / (dx2 + dx3));
+    int I;                                      // HVAL interval (0-based), INTRVL bisection for N = 4
+    if (T < X[0]) I = 0; else if (T > X[3]) I = 2;
+    else { I = T < X[2] ? (T < X[1] ? 0 : 1) : 2; }
+    int err = 0;
+    double sig = sigs_interval(X[I + 1] - X[I], Y[I], Y[I + 1], YP[I], YP[I + 1], err);
+    if (err == 0) return hval_interval(T, X[I], X[I + 1], Y[I], Y[I + 1], YP[I], YP[I + 1], sig);
+    // linint (interpolation_module.f90:25-59), n = 4
+    int jlo = 1, jhi = 4;
+    for (;;) { int k = (jhi + jlo) / 2; if (X[k - 1] > T) jhi = k; else jlo = k; if (jhi - jlo == 1) break; }
+    double m = (Y[jlo - 1] - Y[jhi - 1]) / (X[jlo - 1] - X[jhi - 1]);
+    double b = Y[jlo - 1] - m * X[jlo - 1];
+    return m * T + b;
+}
+
+// WCTS_ITPI (hydro:2577-2689): 4-level profile at 3 times -> spline at P_z{b,c,f}
+// -> time polynomial.  v = 1,2,3: value at ix(v); v = 4: (b + 4c + f)/6.
+template <class T, bool W>
+LT_DEV double wcts(const LtDev& D, const T* fld, int L, const Stencil& s, int grid, int4 und, const Column& col,
+                   int deplvl, double P_zb, double P_zc, double P_zf, int v)
+{
+    double zb[4], zc[4], zf[4], vb[4], vc[4], vf[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int k = deplvl - 1 + i;
+        double sc = W ? D.SCW[k] : D.SC[k], cs = W ? D.CSW[k] : D.CS[k];
+        zb[i] = zlevel(D, col.zb, col.depth, sc, cs);
+        zc[i] = zlevel(D, col.zc, col.depth, sc, cs);
+        zf[i] = zlevel(D, col.zf, col.depth, sc, cs);
+        gather_bcf<T>(D, fld, L, k, s, grid, und, vb[i], vc[i], vf[i]);
+    }
+    double P_vb = spline4_eval(zb, vb, P_zb);
+    double P_vc = spline4_eval(zc, vc, P_zc);
+    double P_vf = D.p == 1 ? 0.0 : spline4_eval(zf, vf, P_zf);
+    if (v <= 3) return time_poly(D, P_vb, P_vc, P_vf, D.ix[v - 1]);
+    double rb = time_poly(D, P_vb, P_vc, P_vf, D.ix[0]);
+    double rc = time_poly(D, P_vb, P_vc, P_vf, D.ix[1]);
+    double rf = time_poly(D, P_vb, P_vc, P_vf, D.ix[2]);
+    return (rb + rc * 4 + rf) / 6.0;
+}
+
+// ---------------------------------------------------------------- Philox ----
+// Philox4x32-10, key = (seed, 0), counter = (id_lo, id_hi, step, block): see
+// include/ltrans_b200.h for the stream layout.
+struct Rng { unsigned id_lo, id_hi, step, seed; };
+LT_DEV uint4 philox(const Rng& g, unsigned block)
+{
+    unsigned c0 = g.id_lo, c1 = g.id_hi, c2 = g.step, c3 = block, k0 = g.seed, k1 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+LT_DEV double u_real3(unsigned w) { return ((double)w + 0.5) / 4294967296.0; }   // random_module.f90:239-246
+LT_DEV double u_real1(unsigned w) { return (double)w / 4294967295.0; }           // random_module.f90:213-220
+// norm_module.f90:25-39 (cosine branch only; PI from the namelist)
+LT_DEV double box_muller(const LtDev& D, unsigned w1, unsigned w2)
+{
+    return sqrt(-2.0 * log(u_real3(w1))) * cos(2.0 * D.P.PI * u_real3(w2));
+}
+
+// -------------------------------------------------------------- boundary ----
+// inpoly (point_in_polygon_module.f90:25-167) on a double2 vertex list.
+LT_DEVN bool inpoly(double x, double y, int n, const double2* __restrict__ e, bool onout)
+{
+    bool on = false;
+    for (int i = 0; i < n; ++i) {                    // :49-57
+        double2 q = __ldg(e + i);
+        if (q.y == y && q.x > x) on = true;
+        if (q.x == x && q.y == y) return !onout;
+    }
+    int crossed = 0;
+    if (on) {                                        // :60-117 (vertex on the ray): literal walk
+        auto hilo = [&](int i1) { double yy = __ldg(e + (i1 - 1)).y; return yy > y ? 1 : (yy < y ? -1 : 0); };
+        bool first = true; int i = 1;
+        for (;;) {
+            if (i > n) break;
+            if (hilo(i) == 0 && __ldg(e + (i - 1)).x > x) {
+                if (first) { i = i + 1; continue; }
+                if (hilo(i - 1) == 0) return !onout;
+                int j = 1;
+                for (;;) {
+                    if ((i + j) == (n + 1)) j = 2 - i;
+                    if (hilo(i + j) != 0) break;
+                    if (__ldg(e + (i + j - 1)).x < x) return !onout;
+                    j = j + 1;
+                }
+                if ((hilo(i - 1) + hilo(i + j)) == 0) crossed = crossed + 1;
+                if (j < 0) break;
+                i = i + j;
+            }
+            first = false;
+            i = i + 1;
+        }
+    }
+    double2 a = __ldg(e);
+    for (int i = 1; i < n; ++i) {                    // :120-160
+        double2 b = __ldg(e + i);
+        bool skip = (a.x <= x && b.x <= x) || (a.y <= y && b.y <= y) || (a.y >= y && b.y >= y);
+        if (!skip) {
+            if (a.x > x && b.x > x) crossed++;
+            else {
+                double m = (b.y - a.y) / (b.x - a.x);
+                double bb = a.y - m * a.x;
+                double ix = (y - bb) / m;
+                if (ix == x) return !onout;
+                if (ix > x) crossed++;
+            }
+        }
+        a = b;
+    }
+    return (crossed & 1) != 0;
+}
+
+// ibounds (boundary_module.f90:1548-1614)
+LT_DEV bool in_any_island(const LtDev& D, double x, double y)
+{
+    if (D.maxisland <= 0) return false;
+    int i = 1, start = 0, isle = __ldg(D.hid);
+    for (;;) {
+        i = i + 1;
+        bool endIsle = (i == D.maxisland) || (__ldg(D.hid + i) != isle);
+        if (endIsle) {
+            if (inpoly(x, y, i - start, D.hxy + start, false)) return true;
+            if (i == D.maxisland) break;
+            start = i; isle = __ldg(D.hid + i);
+        }
+    }
+    return false;
+}
+
+// intersect_reflect (boundary_module.f90:1620-1902): nearest intersection of the
+// move (Xpos,Ypos)->(nXpos,nYpos) with any boundary segment, mirror image of the end
+// point, strict `<` nearest with first index winning.
+struct Hit { double ix, iy, rx, ry; int seg; bool water; };
+LT_DEVN bool intersect_reflect(const LtDev& D, double Xpos, double Ypos, double nXpos, double nYpos,
+                               int skipbound, Hit& h)
+{
+    double xhigh = fmax(Xpos, nXpos), xlow = fmin(Xpos, nXpos), yhigh = fmax(Ypos, nYpos), ylow = fmin(Ypos, nYpos);
+    double dtest = 999999.;
+    bool found = false;
+    double rPx = 0.0, rPy = 0.0;         // ledger 19: kept from the previous segment when dist1 == dist2
+    for (int i = 0; i < D.nbounds; ++i) {
+        if (i == skipbound) continue;
+        const double2* sp = reinterpret_cast<const double2*>(D.seg + i);
+        double2 s1_ = __ldg(sp), s2_ = __ldg(sp + 1);
+        double bcx1 = s1_.x, bcy1 = s1_.y, bcx2 = s2_.x, bcy2 = s2_.y;
+        if ((bcx1 > xhigh && bcx2 > xhigh) || (bcx1 < xlow && bcx2 < xlow) ||
+            (bcy1 > yhigh && bcy2 > yhigh) || (bcy1 < ylow && bcy2 < ylow)) continue;
+        double bxhigh = fmax(bcx1, bcx2), bxlow = fmin(bcx1, bcx2), byhigh = fmax(bcy1, bcy2), bylow = fmin(bcy1, bcy2);
+        double ix, iy, rx1, ry1, rx2, ry2;
+        int kind;           // 0 none, 1 mirror in x, 2 mirror in y, 3 general mirror
+        double Mbc = 0.0, dPBC = 0.0;
+        if (bcx1 == bcx2 || nXpos == Xpos) {
+            if (bcx1 == bcx2 && nXpos == Xpos) continue;
+            if (bcx1 == bcx2 && nYpos == Ypos) {
+                ix = bcx1; iy = nYpos; kind = 1;
+                dPBC = sqrt((ix - nXpos) * (ix - nXpos) + (iy - nYpos) * (iy - nYpos));
+            } else if (nXpos == Xpos && bcy1 == bcy2) {
+                ix = nXpos; iy = bcy1; kind = 2;
+                dPBC = sqrt((ix - nXpos) * (ix - nXpos) + (iy - nYpos) * (iy - nYpos));
+            } else if (bcx1 == bcx2 && nYpos != Ypos) {
+                double Mp = (nYpos - Ypos) / (nXpos - Xpos), Bp = Ypos - Mp * Xpos;
+                ix = bcx1; iy = Mp * ix + Bp; kind = 1;
+                dPBC = nXpos - ix;
+            } else if (nXpos == Xpos && bcy1 != bcy2) {
+                Mbc = (bcy2 - bcy1) / (bcx2 - bcx1);
+                double Bbc = bcy2 - Mbc * bcx2;
+                ix = nXpos; iy = Mbc * ix + Bbc; kind = 3;
+            } else continue;
+        } else {
+            Mbc = (bcy2 - bcy1) / (bcx2 - bcx1);
+            double Bbc = bcy2 - Mbc * bcx2;
+            double Mp = (nYpos - Ypos) / (nXpos - Xpos), Bp = Ypos - Mp * Xpos;
+            ix = (Bbc - Bp) / (Mp - Mbc);
+            iy = Mp * ix + Bp;
+            if (Mbc == 0.0) { iy = byhigh; kind = 2; dPBC = nYpos - bcy1; } else kind = 3;
+        }
+        bool inbox = ix <= xhigh && ix >= xlow && iy <= yhigh && iy >= ylow &&
+                     ix <= bxhigh && ix >= bxlow && iy <= byhigh && iy >= bylow;
+        if (!inbox) continue;
+        if (kind == 1) { rx1 = nXpos + (2.0 * dPBC); ry1 = nYpos; rx2 = nXpos - (2.0 * dPBC); ry2 = nYpos; }
+        else if (kind == 2) { rx1 = nXpos; ry1 = nYpos + (2.0 * dPBC); rx2 = nXpos; ry2 = nYpos - (2.0 * dPBC); }
+        else {
+            double distBC = sqrt((bcx1 - bcx2) * (bcx1 - bcx2) + (bcy1 - bcy2) * (bcy1 - bcy2));
+            double crossk = ((nXpos - bcx1) * (bcy2 - bcy1)) - ((bcx2 - bcx1) * (nYpos - bcy1));
+            dPBC = sqrt(crossk * crossk) / distBC;
+            double mP = -1.0 / Mbc, bP = nYpos - mP * nXpos;
+            double rr = sqrt(((2.0 * dPBC) * (2.0 * dPBC)) / (1.0 + mP * mP));
+            rx1 = rr + nXpos; ry1 = mP * rx1 + bP;
+            rx2 = rr * -1.0 + nXpos; ry2 = mP * rx2 + bP;
+        }
+        double dist1 = sqrt((ix - rx1) * (ix - rx1) + (iy - ry1) * (iy - ry1));
+        double dist2 = sqrt((ix - rx2) * (ix - rx2) + (iy - ry2) * (iy - ry2));
+        if (dist1 < dist2) { rPx = rx1; rPy = ry1; } else if (dist1 > dist2) { rPx = rx2; rPy = ry2; }
+        double d = sqrt((Xpos - ix) * (Xpos - ix) + (Ypos - iy) * (Ypos - iy));
+        if (d < dtest) {
+            h.ix = ix; h.iy = iy; h.rx = rPx; h.ry = rPy; h.seg = i; h.water = !__ldg(D.land + i);
+            dtest = d; found = true;
+        }
+    }
+    return found;
+}
+
+// ------------------------------------------------------------ settlement ----
+// testSettlement / psettle / hsettle (settlement_module.f90:485-622).  Polygon edge
+// columns 4,5 are contiguous per column (Fortran (pedges,5) column-major), so inpoly
+// reads x and y from two arrays here.
+LT_DEVN bool inpoly_cols(double x, double y, int n, const double* __restrict__ ex, const double* __restrict__ ey, bool onout)
+{
+    bool on = false;
+    for (int i = 0; i < n; ++i) {
+        double qx = __ldg(ex + i), qy = __ldg(ey + i);
+        if (qy == y && qx > x) on = true;
+        if (qx == x && qy == y) return !onout;
+    }
+    int crossed = 0;
+    if (on) {
+        auto hilo = [&](int i1) { double yy = __ldg(ey + (i1 - 1)); return yy > y ? 1 : (yy < y ? -1 : 0); };
+        bool first = true; int i = 1;
+        for (;;) {
+            if (i > n) break;
+            if (hilo(i) == 0 && __ldg(ex + (i - 1)) > x) {
+                if (first) { i = i + 1; continue; }
+                if (hilo(i - 1) == 0) return !onout;
+                int j = 1;
+                for (;;) {
+                    if ((i + j) == (n + 1)) j = 2 - i;
+                    if (hilo(i + j) != 0) break;
+                    if (__ldg(ex + (i + j - 1)) < x) return !onout;
+                    j = j + 1;
+                }
+                if ((hilo(i - 1) + hilo(i + j)) == 0) crossed = crossed + 1;
+                if (j < 0) break;
+                i = i + j;
+            }
+            first = false;
+            i = i + 1;
+        }
+    }
+    double ax = __ldg(ex), ay = __ldg(ey);
+    for (int i = 1; i < n; ++i) {
+        double bx = __ldg(ex + i), by = __ldg(ey + i);
+        bool skip = (ax <= x && bx <= x) || (ay <= y && by <= y) || (ay >= y && by >= y);
+        if (!skip) {
+            if (ax > x && bx > x) crossed++;
+            else {
+                double m = (by - ay) / (bx - ax);
+                double bb = ay - m * ax;
+                double ixx = (y - bb) / m;
+                if (ixx == x) return !onout;
+                if (ixx > x) crossed++;
+            }
+        }
+        ax = bx; ay = by;
+    }
+    return (crossed & 1) != 0;
+}
+
+LT_DEVN int test_settlement(const LtDev& D, double P_age, int R_ele, double Px, double Py)
+{
+    if (!(P_age >= D.P.pediage)) return 0;           // settletime = P_pediage (behavior:154)
+    int polyin = 0, pidx = -1;
+    for (int q = __ldg(D.elepoly_ptr + R_ele - 1); q < __ldg(D.elepoly_ptr + R_ele); ++q) {
+        int pi = __ldg(D.elepoly_idx + q);
+        int start = __ldg(D.poly_start + pi), size = __ldg(D.poly_size + pi);
+        const double* c1 = D.polys, *c2 = D.polys + D.pedges, *c3 = c2 + D.pedges, *c4 = c3 + D.pedges, *c5 = c4 + D.pedges;
+        double cx = __ldg(c2 + start - 1), cy = __ldg(c3 + start - 1);
+        double dis = sqrt((Px - cx) * (Px - cx) + (Py - cy) * (Py - cy));
+        if (dis > __ldg(D.poly_maxdis + pi)) continue;
+        if (inpoly_cols(Px, Py, size, c4 + start - 1, c5 + start - 1, false)) {
+            polyin = (int)llrint(__ldg(c1 + start - 1)); pidx = pi; break;
+        }
+    }
+    if (polyin <= 0) return 0;
+    if (D.P.holesExist) {
+        for (int q = __ldg(D.polyhole_ptr + pidx); q < __ldg(D.polyhole_ptr + pidx + 1); ++q) {
+            int hi = __ldg(D.polyhole_idx + q);
+            int start = __ldg(D.hole_start + hi), size = __ldg(D.hole_size + hi);
+            const double* c2 = D.holes + D.hedges, *c3 = c2 + D.hedges, *c4 = c3 + D.hedges, *c5 = c4 + D.hedges;
+            double cx = __ldg(c2 + start - 1), cy = __ldg(c3 + start - 1);
+            double dis = sqrt((Px - cx) * (Px - cx) + (Py - cy) * (Py - cy));
+            if (dis > __ldg(D.hole_maxdis + hi)) continue;
+            if (inpoly_cols(Px, Py, size, c4 + start - 1, c5 + start - 1, true)) return 0;   // onin = .FALSE.
+        }
+    }
+    return polyin;
+}

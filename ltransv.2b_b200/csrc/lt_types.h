@@ -1,0 +1,64 @@
+// lt_types.h -- device-side view of one context (kernel argument, lives in the
+// constant bank).  Layouts are chosen for the B200 memory system, not copied from
+// the reference's (3, node, level) Fortran arrays:
+//   * hydro fields: [node][level][4 ring slots] -- the three time levels a
+//     particle needs for one (node, level) sit in ONE 16-byte (f32) / 32-byte (f64)
+//     chunk, so a 4-corner x 4-level stencil is 16 LDG.128 instead of 48 scalar
+//     gathers, and the 4th component is the slot being refilled by the copy stream.
+//   * element tables: corner coordinates packed as 8 doubles per element (two
+//     32-byte sectors); adjacency row-major [element][10].
+//   * particles: structure of arrays, one thread per particle.
+#pragma once
+#include <stdint.h>
+#include "../../include/ltrans_b200.h"
+
+#define LT_MAXLEV 64            // us <= 63, ws <= 64
+
+struct LtGridTab {              // one of the rho / u / v grids
+    const double* ele;          // [nE][8]  x0..x3,y0..y3 of the element corners
+    const int4*   node;         // [nE]     0-based node ids of the corners (RE/UE/VE - 1)
+    const int*    adj;          // [nE][10] 1-based neighbour element ids, 0 = none
+    const uint8_t* mask;        // [nodes]  only read when FreeSlip
+    int nE, nodes;
+};
+
+struct LtDev {
+    ltgpu_params P;
+    LtGridTab R, U, V;
+    const double* depth;        // [rho_nodes]
+    const double* angle;        // [rho_nodes]
+    // fields: [node][level][4]; element type float or double (P.field_dtype)
+    const void *zeta, *u, *v, *w, *kh, *salt, *temp;
+    int sb, sc, sf;             // ring slot holding the back / centre / forward record
+    // boundary
+    const double4* seg;         // [nbounds] x1,y1,x2,y2
+    const uint8_t* land;        // [nbounds]
+    const double2* bxy;         // [maxbound] closed main polygon
+    const double2* hxy;         // [maxisland] closed island polygons, concatenated
+    const int* hid;             // [maxisland]
+    int nbounds, maxbound, maxisland;
+    // habitat (CSR)
+    const double* polys; const double* holes; int pedges, hedges, npoly, nhole;
+    const int *poly_start, *poly_size, *hole_start, *hole_size;
+    const double *poly_maxdis, *hole_maxdis;
+    const int *elepoly_ptr, *elepoly_idx, *polyhole_ptr, *polyhole_idx;
+    // particles (SoA)
+    double *x, *y, *z, *age, *dob, *lifespan, *psalt, *ptemp, *timer, *sprev, *zprev;
+    int *r_ele, *u_ele, *v_ele, *hitB, *hitL, *endpoly;
+    uint8_t* flags;             // bit0 settled, bit1 dead, bit2 oob, bit3 bottom (behaviour 7)
+    int8_t* behave;             // P_behave
+    int n; long long first_id;
+    // events
+    ltgpu_event* ev; int* nev; int evcap; int* bad;
+    // VTurb scratch: 7 arrays, element k of thread t at [k*vt_stride + t]
+    double* vt; long long vt_stride; int vt_p2;
+    // this step
+    int p, it; unsigned gstep;
+    double ex[3], ix[3];
+    double SC[LT_MAXLEV], CS[LT_MAXLEV], SCW[LT_MAXLEV], CSW[LT_MAXLEV];
+};
+
+#define LT_F_SETTLED 1
+#define LT_F_DEAD    2
+#define LT_F_OOB     4
+#define LT_F_BOTTOM  8

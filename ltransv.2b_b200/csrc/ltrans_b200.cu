@@ -1,0 +1,626 @@
+// ltrans_b200.cu -- C ABI (include/ltrans_b200.h) + kernels of the B200-native
+// LTRANS v.2b particle step.  Build: nvcc -gencode arch=compute_100a,code=sm_100a.
+//
+// One context = one GPU.  Streams: `compute` runs the particle step; `copy` refills
+// the spare hydro ring slot (pinned staging -> H2D -> transpose/mask kernel) while the
+// loop runs; an event fences the slot before the step that first reads it.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "lt_step.cuh"
+
+// ------------------------------------------------------------------ kernels --
+template <class T>
+__global__ void __launch_bounds__(128) k_step(const __grid_constant__ LtDev D)
+{
+    size_t tslot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t n = tslot; n < (size_t)D.n; n += stride) step_particle<T>(D, (int)n, tslot);
+}
+
+// one ROMS record [level][node] (+ mask multiply, hydro:1371-1403) -> ring slot of the
+// [node][level][4] device layout.  Block = 32 nodes x 8 levels through shared memory so
+// both the read (node-fastest) and the write (level-fastest) are coalesced.
+template <class TI, class TO>
+__global__ void k_fill_slot(const TI* __restrict__ in, const uint8_t* __restrict__ mask, TO* __restrict__ out,
+                            int nodes, int L, int slot)
+{
+    __shared__ double tile[32][33];
+    int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y) {
+        int n = n0 + threadIdx.x, k = k0 + kk;
+        if (n < nodes && k < L) tile[kk][threadIdx.x] = (double)in[(size_t)k * nodes + n] * (double)mask[n];
+    }
+    __syncthreads();
+    for (int nn = threadIdx.y; nn < 32; nn += blockDim.y) {
+        int n = n0 + nn, k = k0 + threadIdx.x;
+        if (n < nodes && k < L) out[((size_t)n * L + k) * 4 + slot] = (TO)tile[threadIdx.x][nn];
+    }
+}
+
+__global__ void k_status(const LtDev D, int* __restrict__ status)
+{   // getStatus behavior_module.f90:554-574
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= D.n) return;
+    int s = D.behave[n]; uint8_t f = D.flags[n];
+    if (f & LT_F_DEAD) s = -1;
+    if (D.P.settlementon && (f & LT_F_SETTLED)) s = -2;
+    if (D.P.OpenOceanBoundary && (f & LT_F_OOB)) s = -3;
+    status[n] = s;
+}
+
+__global__ void k_stats(const LtDev D, double last_ix3, unsigned long long* __restrict__ out)
+{
+    unsigned long long c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < D.n; n += gridDim.x * blockDim.x) {
+        uint8_t f = D.flags[n];
+        bool settled = D.P.settlementon && (f & LT_F_SETTLED), out_ = D.P.OpenOceanBoundary && (f & LT_F_OOB);
+        c[0] += settled; c[1] += (f & LT_F_DEAD) != 0; c[2] += (f & LT_F_OOB) != 0;
+        c[3] += (unsigned)D.hitL[n]; c[4] += (unsigned)D.hitB[n];
+        if (last_ix3 <= D.dob[n]) c[7]++;
+        else if (!settled && !(D.P.mortality && (f & LT_F_DEAD)) && !out_) c[6]++;
+    }
+    for (int k = 0; k < 8; ++k) {
+        unsigned long long v = c[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(out + k, v);
+    }
+}
+
+// setEle first=.TRUE. (hydro:1436-1457): whole-grid scan, one thread per particle.
+// gridcell without checkele keeps scanning after an on-edge hit whose crossing total is
+// even (the inner `exit`), so the answer is the first definite hit, else the last soft one;
+// a point on a shared edge is a definite hit of the lower-numbered element, which is what
+// a first-hit scan returns, so the two coincide except for degenerate (zero-area) elements.
+__global__ void k_locate(const LtDev D, LtGridTab G, int* __restrict__ ele)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= D.n) return;
+    double X = D.x[n], Y = D.y[n];
+    int found = 0;
+    for (int e = 0; e < G.nE; ++e)
+        if (gridcell(G.ele + (size_t)e * 8, X, Y)) { found = e + 1; break; }
+    ele[n] = found;
+}
+
+__global__ void k_fill_i32(int* p, int v, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// --------------------------------------------------------------- context -----
+struct ltgpu_ctx {
+    ltgpu_params prm;
+    int device = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t slot_ready[4] = {nullptr, nullptr, nullptr, nullptr}, slot_free = nullptr, t0 = nullptr, t1 = nullptr;
+    LtDev D;
+    std::vector<void*> owned;                // every cudaMalloc, freed in destroy
+    // grid sizes
+    int rho_nodes = 0, u_nodes = 0, v_nodes = 0;
+    size_t esz = 4;                          // bytes per field element on the device
+    uint8_t *m_rho = nullptr, *m_u = nullptr, *m_v = nullptr;      // masks (always uploaded: used by the fill kernel)
+    // hydro ring
+    int npushed = 0, pending_slot = -1, spare = 3;
+    void* h_stage[2] = {nullptr, nullptr}; void* d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0; int stage_i = 0;
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    // events
+    std::vector<ltgpu_event> host_events;
+    int* d_bad = nullptr; int* d_nev = nullptr; int evcap = 1 << 20; int ev_read = 0;
+    unsigned long long* d_stats = nullptr; int* d_status = nullptr;
+    double last_ix3 = -1e300;
+    long long launches = 0;
+    std::string err;
+    bool have_grid = false, have_bounds = false, have_particles = false, have_habitat = false;
+    int nthreads_grid = 0;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return LTGPU_E_CUDA; } } while (0)
+#define ARG(cond, msg) do { if (!(cond)) { ctx->err = msg; return LTGPU_E_ARG; } } while (0)
+
+template <class T>
+static int32_t dalloc(ltgpu_ctx* ctx, T** p, size_t count)
+{
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    ctx->owned.push_back(q);
+    *p = (T*)q;
+    return LTGPU_OK;
+}
+template <class T>
+static int32_t upload(ltgpu_ctx* ctx, const T** dst, const T* src, size_t count)
+{
+    T* q = nullptr;
+    int32_t rc = dalloc(ctx, &q, count);
+    if (rc) return rc;
+    if (count) CK(cudaMemcpyAsync(q, src, count * sizeof(T), cudaMemcpyHostToDevice, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));       // src may be a temporary
+    *dst = q;
+    return LTGPU_OK;
+}
+#define TRY(x) do { int32_t rc_ = (x); if (rc_) return rc_; } while (0)
+
+// ----------------------------------------------------------- hydro refill ----
+template <class TI>
+static void fill_all(ltgpu_ctx* ctx, const uint8_t* dbase, const size_t off[7], bool have_st, int slot, cudaStream_t s)
+{
+    LtDev& D = ctx->D;
+    int us = ctx->prm.us, ws = ctx->prm.ws;
+    struct { int nodes, L; const uint8_t* mask; void* out; } f[7] = {
+        {ctx->rho_nodes, 1, ctx->m_rho, (void*)D.zeta}, {ctx->u_nodes, us, ctx->m_u, (void*)D.u},
+        {ctx->v_nodes, us, ctx->m_v, (void*)D.v}, {ctx->rho_nodes, ws, ctx->m_rho, (void*)D.w},
+        {ctx->rho_nodes, ws, ctx->m_rho, (void*)D.kh}, {ctx->rho_nodes, us, ctx->m_rho, (void*)D.salt},
+        {ctx->rho_nodes, us, ctx->m_rho, (void*)D.temp}};
+    for (int i = 0; i < 7; ++i) {
+        if (i >= 5 && !have_st) break;
+        dim3 blk(32, 8), grd((f[i].nodes + 31) / 32, (f[i].L + 31) / 32);
+        const TI* in = (const TI*)(dbase + off[i]);
+        if (ctx->esz == 4) k_fill_slot<TI, float><<<grd, blk, 0, s>>>(in, f[i].mask, (float*)f[i].out, f[i].nodes, f[i].L, slot);
+        else k_fill_slot<TI, double><<<grd, blk, 0, s>>>(in, f[i].mask, (double*)f[i].out, f[i].nodes, f[i].L, slot);
+        ctx->launches++;
+    }
+}
+
+extern "C" {
+
+int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
+{
+    if (!prm || !out) return LTGPU_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+        return LTGPU_E_NODEVICE;                   // no CPU fallback
+    ltgpu_ctx* ctx = new ltgpu_ctx();
+    ctx->prm = *prm; ctx->device = device;
+    memset(&ctx->D, 0, sizeof(LtDev));
+    ctx->D.P = *prm;
+    if (prm->us < 5 || prm->us >= LT_MAXLEV || prm->ws != prm->us + 1 || prm->idt <= 0 || prm->dt < prm->idt ||
+        prm->z0 == 0.0 || prm->Vtransform < 1 || prm->Vtransform > 3 ||
+        (prm->field_dtype != LTGPU_F32 && prm->field_dtype != LTGPU_F64) || prm->rng_mode != LTGPU_RNG_PHILOX) {
+        delete ctx; return LTGPU_E_ARG;            // z0 == 0 is `stop 'dividing by 0'` LTRANS.f90:1512
+    }
+    ctx->esz = prm->field_dtype == LTGPU_F32 ? 4 : 8;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return LTGPU_E_NODEVICE; }
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, device) != cudaSuccess) { delete ctx; return LTGPU_E_NODEVICE; }
+    ctx->nthreads_grid = pr.multiProcessorCount * 1024;
+    if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LTGPU_E_CUDA; }
+    for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->slot_ready[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->slot_free, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming);
+    cudaEventCreate(&ctx->t0); cudaEventCreate(&ctx->t1);
+    ctx->D.sb = 0; ctx->D.sc = 1; ctx->D.sf = 2; ctx->spare = 3;
+    *out = ctx;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_destroy(ltgpu_ctx* ctx)
+{
+    if (!ctx) return LTGPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->owned) cudaFree(p);
+    for (int i = 0; i < 2; ++i) { if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]); if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]); }
+    for (int i = 0; i < 4; ++i) if (ctx->slot_ready[i]) cudaEventDestroy(ctx->slot_ready[i]);
+    if (ctx->slot_free) cudaEventDestroy(ctx->slot_free);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    delete ctx;
+    return LTGPU_OK;
+}
+
+const char* ltgpu_last_error(const ltgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+static int32_t make_gridtab(ltgpu_ctx* ctx, LtGridTab* G, int nE, int nodes, const int32_t* E, const int32_t* Adj,
+                            const double* nx, const double* ny, const uint8_t* dmask)
+{
+    std::vector<double> ele((size_t)nE * 8);
+    std::vector<int4> nd(nE);
+    std::vector<int> adj((size_t)nE * 10);
+    for (int e = 0; e < nE; ++e) {
+        int q[4];
+        for (int i = 0; i < 4; ++i) {
+            q[i] = E[4 * (size_t)e + i] - 1;
+            if (q[i] < 0 || q[i] >= nodes) { ctx->err = "element node id out of range"; return LTGPU_E_ARG; }
+            ele[(size_t)e * 8 + i] = nx[q[i]]; ele[(size_t)e * 8 + 4 + i] = ny[q[i]];     // hydro:561-580
+        }
+        nd[e] = make_int4(q[0], q[1], q[2], q[3]);
+        for (int i = 0; i < 10; ++i) {
+            int a = Adj[(size_t)i * nE + e];                       // Fortran (nE,10) column-major
+            if (a < 0 || a > nE) { ctx->err = "adjacency id out of range"; return LTGPU_E_ARG; }
+            adj[(size_t)e * 10 + i] = a;
+        }
+    }
+    TRY(upload(ctx, &G->ele, ele.data(), ele.size()));
+    TRY(upload(ctx, &G->node, nd.data(), nd.size()));
+    TRY(upload(ctx, &G->adj, adj.data(), adj.size()));
+    G->mask = dmask; G->nE = nE; G->nodes = nodes;
+    return LTGPU_OK;
+}
+
+static int32_t upload_mask(ltgpu_ctx* ctx, uint8_t** d, const int32_t* m, int n)
+{
+    std::vector<uint8_t> t(n);
+    for (int i = 0; i < n; ++i) t[i] = m[i] != 0;
+    const uint8_t* q = nullptr;
+    TRY(upload(ctx, &q, t.data(), (size_t)n));
+    *d = (uint8_t*)q;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_set_grid(ltgpu_ctx* ctx, int32_t vi, int32_t uj, int32_t ui, int32_t vj,
+    const double* rx, const double* ry, const double* ux, const double* uy,
+    const double* vx, const double* vy, const double* depth, const double* angle,
+    const int32_t* rho_mask, const int32_t* u_mask, const int32_t* v_mask,
+    const double* SC, const double* CS, const double* SCW, const double* CSW,
+    const int32_t* RE, const int32_t* UE, const int32_t* VE,
+    int32_t nRE, int32_t nUE, int32_t nVE,
+    const int32_t* rAdj, const int32_t* uAdj, const int32_t* vAdj)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(!ctx->have_grid, "set_grid called twice");
+    ARG(rx && ry && ux && uy && vx && vy && depth && angle && rho_mask && u_mask && v_mask && SC && CS && SCW && CSW &&
+        RE && UE && VE && rAdj && uAdj && vAdj, "set_grid: null array");
+    ARG(vi > 1 && uj > 1 && ui > 0 && vj > 0 && nRE > 0 && nUE > 0 && nVE > 0, "set_grid: bad sizes");
+    CK(cudaSetDevice(ctx->device));
+    ctx->rho_nodes = vi * uj; ctx->u_nodes = ui * uj; ctx->v_nodes = vi * vj;
+    TRY(upload_mask(ctx, &ctx->m_rho, rho_mask, ctx->rho_nodes));
+    TRY(upload_mask(ctx, &ctx->m_u, u_mask, ctx->u_nodes));
+    TRY(upload_mask(ctx, &ctx->m_v, v_mask, ctx->v_nodes));
+    LtDev& D = ctx->D;
+    TRY(make_gridtab(ctx, &D.R, nRE, ctx->rho_nodes, RE, rAdj, rx, ry, ctx->m_rho));
+    TRY(make_gridtab(ctx, &D.U, nUE, ctx->u_nodes, UE, uAdj, ux, uy, ctx->m_u));
+    TRY(make_gridtab(ctx, &D.V, nVE, ctx->v_nodes, VE, vAdj, vx, vy, ctx->m_v));
+    TRY(upload(ctx, &D.depth, depth, (size_t)ctx->rho_nodes));
+    TRY(upload(ctx, &D.angle, angle, (size_t)ctx->rho_nodes));
+    int us = ctx->prm.us, ws = ctx->prm.ws;
+    for (int k = 0; k < us; ++k) { D.SC[k] = SC[k]; D.CS[k] = CS[k]; }
+    for (int k = 0; k < ws; ++k) { D.SCW[k] = SCW[k]; D.CSW[k] = CSW[k]; }
+    // hydro ring: [node][level][4]
+    size_t e = ctx->esz, rn = ctx->rho_nodes, un = ctx->u_nodes, vn = ctx->v_nodes;
+    struct { const void** p; size_t count; } f[] = {
+        {&D.zeta, rn * 4}, {&D.u, un * us * 4}, {&D.v, vn * us * 4}, {&D.w, rn * ws * 4}, {&D.kh, rn * ws * 4},
+        {&D.salt, rn * us * 4}, {&D.temp, rn * us * 4}};
+    for (auto& q : f) {
+        uint8_t* p = nullptr;
+        TRY(dalloc(ctx, &p, q.count * e));
+        CK(cudaMemsetAsync(p, 0, q.count * e, ctx->compute));
+        *q.p = p;
+    }
+    // staging: one record = zeta + u + v + w + aks + salt + temp, at the host dtype (<= 8 B)
+    ctx->stage_bytes = (rn + un * us + vn * us + 2 * rn * ws + 2 * rn * us) * 8;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaMallocHost(&ctx->h_stage[i], ctx->stage_bytes));
+        void* d = nullptr; CK(cudaMalloc(&d, ctx->stage_bytes)); ctx->owned.push_back(d); ctx->d_stage[i] = d;
+    }
+    CK(cudaStreamSynchronize(ctx->compute));
+    ctx->have_grid = true;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_set_bounds(ltgpu_ctx* ctx, int32_t nbounds, const double* bnd_x, const double* bnd_y, const int32_t* land,
+    int32_t maxbound, const double* bx, const double* by, int32_t maxisland, const double* hx, const double* hy,
+    const int32_t* hid)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(nbounds >= 0 && maxbound >= 0 && maxisland >= 0, "set_bounds: bad sizes");
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D;
+    std::vector<double4> seg(nbounds); std::vector<uint8_t> ld(nbounds);
+    for (int i = 0; i < nbounds; ++i) {
+        seg[i] = make_double4(bnd_x[2 * i], bnd_y[2 * i], bnd_x[2 * i + 1], bnd_y[2 * i + 1]);
+        ld[i] = land[i] != 0;
+    }
+    std::vector<double2> b(maxbound), h(maxisland);
+    for (int i = 0; i < maxbound; ++i) b[i] = make_double2(bx[i], by[i]);
+    for (int i = 0; i < maxisland; ++i) h[i] = make_double2(hx[i], hy[i]);
+    TRY(upload(ctx, &D.seg, seg.data(), seg.size()));
+    TRY(upload(ctx, &D.land, ld.data(), ld.size()));
+    TRY(upload(ctx, &D.bxy, b.data(), b.size()));
+    TRY(upload(ctx, &D.hxy, h.data(), h.size()));
+    TRY(upload(ctx, &D.hid, hid, (size_t)maxisland));
+    D.nbounds = nbounds; D.maxbound = maxbound; D.maxisland = maxisland;
+    ctx->have_bounds = true;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_set_habitat(ltgpu_ctx* ctx, int32_t pedges, const double* polys, int32_t hedges, const double* holes,
+    int32_t npoly, const int32_t* poly_id, const int32_t* poly_start, const int32_t* poly_size, const double* poly_maxdis,
+    int32_t nhole, const int32_t* hole_id, const int32_t* hole_start, const int32_t* hole_size, const double* hole_maxdis,
+    const int32_t* elepoly_ptr, const int32_t* elepoly_idx, const int32_t* polyhole_ptr, const int32_t* polyhole_idx)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->have_grid, "set_habitat before set_grid");
+    (void)poly_id; (void)hole_id;
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D;
+    TRY(upload(ctx, &D.polys, polys, (size_t)pedges * 5));
+    TRY(upload(ctx, &D.holes, holes, (size_t)hedges * 6));
+    TRY(upload(ctx, &D.poly_start, poly_start, (size_t)npoly));
+    TRY(upload(ctx, &D.poly_size, poly_size, (size_t)npoly));
+    TRY(upload(ctx, &D.poly_maxdis, poly_maxdis, (size_t)npoly));
+    TRY(upload(ctx, &D.hole_start, hole_start, (size_t)nhole));
+    TRY(upload(ctx, &D.hole_size, hole_size, (size_t)nhole));
+    TRY(upload(ctx, &D.hole_maxdis, hole_maxdis, (size_t)nhole));
+    TRY(upload(ctx, &D.elepoly_ptr, elepoly_ptr, (size_t)D.R.nE + 1));
+    TRY(upload(ctx, &D.elepoly_idx, elepoly_idx, (size_t)elepoly_ptr[D.R.nE]));
+    TRY(upload(ctx, &D.polyhole_ptr, polyhole_ptr, (size_t)npoly + 1));
+    TRY(upload(ctx, &D.polyhole_idx, polyhole_idx, (size_t)polyhole_ptr[npoly]));
+    D.pedges = pedges; D.hedges = hedges; D.npoly = npoly; D.nhole = nhole;
+    ctx->have_habitat = true;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
+    const double* x, const double* y, const double* z, const double* dob, const int32_t* startpoly,
+    const int32_t* r_ele, const int32_t* u_ele, const int32_t* v_ele)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->have_grid, "set_particles before set_grid");
+    ARG(!ctx->have_particles, "set_particles called twice");
+    ARG(n > 0 && x && y && z && dob, "set_particles: null array");
+    (void)startpoly;                               // never changes: stays with the host (LTRANS.f90:650)
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D;
+    D.n = n; D.first_id = first_id;
+    size_t N = (size_t)n;
+    double** dd[] = {&D.x, &D.y, &D.z, &D.age, &D.dob, &D.lifespan, &D.psalt, &D.ptemp, &D.timer, &D.sprev, &D.zprev};
+    for (auto p : dd) { TRY(dalloc(ctx, p, N)); CK(cudaMemsetAsync(*p, 0, N * 8, ctx->compute)); }
+    int** ii[] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly};
+    for (auto p : ii) { TRY(dalloc(ctx, p, N)); CK(cudaMemsetAsync(*p, 0, N * 4, ctx->compute)); }
+    TRY(dalloc(ctx, &D.flags, N)); TRY(dalloc(ctx, &D.behave, N));
+    CK(cudaMemsetAsync(D.flags, ctx->prm.Behavior == 7 ? LT_F_BOTTOM : 0, N, ctx->compute));   // behavior:113
+    CK(cudaMemsetAsync(D.behave, ctx->prm.Behavior, N, ctx->compute));                          // behavior:118
+    CK(cudaMemcpyAsync(D.x, x, N * 8, cudaMemcpyHostToDevice, ctx->compute));
+    CK(cudaMemcpyAsync(D.y, y, N * 8, cudaMemcpyHostToDevice, ctx->compute));
+    CK(cudaMemcpyAsync(D.z, z, N * 8, cudaMemcpyHostToDevice, ctx->compute));
+    CK(cudaMemcpyAsync(D.dob, dob, N * 8, cudaMemcpyHostToDevice, ctx->compute));
+    if (r_ele && u_ele && v_ele) {
+        CK(cudaMemcpyAsync(D.r_ele, r_ele, N * 4, cudaMemcpyHostToDevice, ctx->compute));
+        CK(cudaMemcpyAsync(D.u_ele, u_ele, N * 4, cudaMemcpyHostToDevice, ctx->compute));
+        CK(cudaMemcpyAsync(D.v_ele, v_ele, N * 4, cudaMemcpyHostToDevice, ctx->compute));
+    } else {
+        int blocks = (n + 127) / 128;
+        k_locate<<<blocks, 128, 0, ctx->compute>>>(D, D.R, D.r_ele);
+        k_locate<<<blocks, 128, 0, ctx->compute>>>(D, D.U, D.u_ele);
+        k_locate<<<blocks, 128, 0, ctx->compute>>>(D, D.V, D.v_ele);
+        ctx->launches += 3;
+    }
+    TRY(dalloc(ctx, &D.ev, (size_t)ctx->evcap)); D.evcap = ctx->evcap;
+    TRY(dalloc(ctx, &ctx->d_nev, 1)); TRY(dalloc(ctx, &ctx->d_bad, 1));
+    D.nev = ctx->d_nev; D.bad = ctx->d_bad;
+    CK(cudaMemsetAsync(ctx->d_nev, 0, 4, ctx->compute));
+    k_fill_i32<<<1, 32, 0, ctx->compute>>>(ctx->d_bad, INT_MAX, 1);
+    TRY(dalloc(ctx, &ctx->d_stats, 8)); TRY(dalloc(ctx, &ctx->d_status, N));
+    // VTurb scratch: 7 arrays of (4*ws + 8) doubles per resident thread
+    int threads = (int)std::min<size_t>((size_t)ctx->nthreads_grid, ((N + 127) / 128) * 128);
+    ctx->nthreads_grid = threads;
+    if (ctx->prm.VTurbOn) {
+        D.vt_p2 = 4 * ctx->prm.ws; D.vt_stride = threads;
+        TRY(dalloc(ctx, &D.vt, (size_t)7 * (D.vt_p2 + 8) * (size_t)threads));
+    }
+    CK(cudaStreamSynchronize(ctx->compute));
+    ctx->have_particles = true;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_push_hydro(ltgpu_ctx* ctx, int32_t dtype, const void* zeta, const void* u, const void* v, const void* w,
+                         const void* aks, const void* salt, const void* temp)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->have_grid, "push_hydro before set_grid");
+    ARG(dtype == LTGPU_F32 || dtype == LTGPU_F64, "push_hydro: bad dtype");
+    ARG(zeta && u && v && w && aks, "push_hydro: null array");
+    bool need_st = ctx->prm.SaltTempOn || ctx->prm.Behavior == 4 || ctx->prm.Behavior == 5 || ctx->prm.Behavior == 7;
+    bool have_st = salt && temp;
+    ARG(have_st || !need_st, "push_hydro: salt/temp required by SaltTempOn / Behavior 4,5,7");
+    ARG(ctx->pending_slot < 0, "push_hydro: previous record not rotated in yet");
+    CK(cudaSetDevice(ctx->device));
+    int slot = ctx->npushed < 3 ? ctx->npushed : ctx->spare;
+    size_t e = dtype == LTGPU_F32 ? 4 : 8, us = ctx->prm.us, ws = ctx->prm.ws;
+    size_t rn = ctx->rho_nodes, un = ctx->u_nodes, vn = ctx->v_nodes;
+    size_t cnt[7] = {rn, un * us, vn * us, rn * ws, rn * ws, rn * us, rn * us}, off[7];
+    const void* src[7] = {zeta, u, v, w, aks, salt, temp};
+    int si = ctx->stage_i; ctx->stage_i ^= 1;
+    CK(cudaEventSynchronize(ctx->stage_done[si]));             // staging buffer free again?
+    uint8_t* hs = (uint8_t*)ctx->h_stage[si];
+    size_t o = 0;
+    for (int i = 0; i < 7; ++i) {
+        off[i] = o;
+        if (i >= 5 && !have_st) continue;
+        memcpy(hs + o, src[i], cnt[i] * e);                    // pageable -> pinned
+        o += (cnt[i] * e + 15) & ~(size_t)15;
+    }
+    // the spare slot may still be read as "back" by steps queued before the last rotate
+    CK(cudaStreamWaitEvent(ctx->copy, ctx->slot_free, 0));
+    CK(cudaMemcpyAsync(ctx->d_stage[si], hs, o, cudaMemcpyHostToDevice, ctx->copy));
+    if (dtype == LTGPU_F32) fill_all<float>(ctx, (const uint8_t*)ctx->d_stage[si], off, have_st, slot, ctx->copy);
+    else fill_all<double>(ctx, (const uint8_t*)ctx->d_stage[si], off, have_st, slot, ctx->copy);
+    CK(cudaEventRecord(ctx->stage_done[si], ctx->copy));
+    CK(cudaEventRecord(ctx->slot_ready[slot], ctx->copy));
+    CK(cudaGetLastError());
+    if (ctx->npushed < 3) CK(cudaStreamWaitEvent(ctx->compute, ctx->slot_ready[slot], 0));
+    else ctx->pending_slot = slot;
+    ctx->npushed++;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_rotate_hydro(ltgpu_ctx* ctx)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->pending_slot >= 0, "rotate_hydro: no pushed record pending");
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D;
+    int old_b = D.sb;
+    D.sb = D.sc; D.sc = D.sf; D.sf = ctx->pending_slot;        // hydro:1080-1082
+    ctx->spare = old_b; ctx->pending_slot = -1;
+    CK(cudaStreamWaitEvent(ctx->compute, ctx->slot_ready[D.sf], 0));
+    CK(cudaEventRecord(ctx->slot_free, ctx->compute));          // steps queued so far were the last readers of old_b
+    return LTGPU_OK;
+}
+
+// ---------------------------------------------------------------- stepping ---
+int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->have_grid && ctx->have_bounds && ctx->have_particles, "step: grid / bounds / particles not set");
+    ARG(ctx->npushed >= 3, "step: fewer than 3 hydro records pushed");
+    ARG(!ctx->prm.settlementon || ctx->have_habitat, "step: settlementon without set_habitat");
+    ARG(p >= 1 && it >= 1, "step: p and it are 1-based");
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D;
+    const int dt = ctx->prm.dt, idt = ctx->prm.idt;
+    D.p = p; D.it = it;
+    D.ex[0] = (double)((p - 2) * dt); D.ex[1] = (double)((p - 1) * dt); D.ex[2] = (double)(p * dt);   // LTRANS.f90:568-571
+    D.ix[0] = D.ex[1] + (double)((it - 2) * idt);                                                      // :588-590
+    D.ix[1] = D.ex[1] + (double)((it - 1) * idt);
+    D.ix[2] = D.ex[1] + (double)(it * idt);
+    D.gstep = (unsigned)((p - 1) * (dt / idt) + it);
+    int blocks = ctx->nthreads_grid / 128;
+    if (ctx->esz == 4) k_step<float><<<blocks, 128, 0, ctx->compute>>>(D);
+    else k_step<double><<<blocks, 128, 0, ctx->compute>>>(D);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    ctx->last_ix3 = D.ix[2];
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_run_external(ltgpu_ctx* ctx, int32_t p)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    int stepIT = ctx->prm.dt / ctx->prm.idt;                   // LTRANS.f90:554
+    for (int it = 1; it <= stepIT; ++it) TRY(ltgpu_step(ctx, p, it));
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_sync(ltgpu_ctx* ctx, int32_t* bad_particle)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy));
+    CK(cudaStreamSynchronize(ctx->compute));
+    int bad = INT_MAX;
+    if (ctx->d_bad) CK(cudaMemcpy(&bad, ctx->d_bad, 4, cudaMemcpyDeviceToHost));
+    if (bad_particle) *bad_particle = bad == INT_MAX ? 0 : bad;
+    if (bad != INT_MAX) { ctx->err = "a particle hit a STOP condition (ErrorFlag outside 1..3)"; return LTGPU_E_PARTICLE; }
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_fetch(ltgpu_ctx* ctx, double* x, double* y, double* z, double* age, int32_t* status,
+    double* salt, double* temp, int32_t* hitBottom, int32_t* hitLand, int32_t* endpoly, double* lifespan,
+    int32_t* r_ele, int32_t* u_ele, int32_t* v_ele)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "fetch before set_particles");
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D; size_t N = D.n; cudaStream_t s = ctx->compute;
+    if (status) { k_status<<<(D.n + 255) / 256, 256, 0, s>>>(D, ctx->d_status); ctx->launches++; }
+    struct { void* h; const void* d; size_t b; } c[] = {
+        {x, D.x, N * 8}, {y, D.y, N * 8}, {z, D.z, N * 8}, {age, D.age, N * 8}, {status, ctx->d_status, N * 4},
+        {salt, D.psalt, N * 8}, {temp, D.ptemp, N * 8}, {hitBottom, D.hitB, N * 4}, {hitLand, D.hitL, N * 4},
+        {endpoly, D.endpoly, N * 4}, {lifespan, D.lifespan, N * 8}, {r_ele, D.r_ele, N * 4}, {u_ele, D.u_ele, N * 4},
+        {v_ele, D.v_ele, N * 4}};
+    for (auto& q : c) if (q.h) CK(cudaMemcpyAsync(q.h, q.d, q.b, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_reset_hits(ltgpu_ctx* ctx)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "reset_hits before set_particles");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->D.hitB, 0, (size_t)ctx->D.n * 4, ctx->compute));     // LTRANS.f90:1662-1665
+    CK(cudaMemsetAsync(ctx->D.hitL, 0, (size_t)ctx->D.n * 4, ctx->compute));
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_stats(ltgpu_ctx* ctx, int64_t counts[8])
+{
+    if (!ctx || !counts) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "stats before set_particles");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->compute));
+    int blocks = std::min((ctx->D.n + 255) / 256, 1184);
+    k_stats<<<blocks, 256, 0, ctx->compute>>>(ctx->D, ctx->last_ix3, ctx->d_stats);
+    ctx->launches++;
+    unsigned long long h[8]; int nev = 0;
+    CK(cudaMemcpyAsync(h, ctx->d_stats, 64, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaMemcpyAsync(&nev, ctx->d_nev, 4, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    for (int k = 0; k < 8; ++k) counts[k] = (int64_t)h[k];
+    counts[5] = (int64_t)(nev - ctx->ev_read) + (int64_t)ctx->host_events.size();
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_drain_events(ltgpu_ctx* ctx, ltgpu_event* buf, int32_t cap, int32_t* n)
+{
+    if (!ctx || !buf || !n || cap < 0) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "drain_events before set_particles");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->compute));
+    int nev = 0;
+    CK(cudaMemcpy(&nev, ctx->d_nev, 4, cudaMemcpyDeviceToHost));
+    nev = std::min(nev, ctx->evcap);
+    if (nev > ctx->ev_read) {
+        size_t old = ctx->host_events.size();
+        ctx->host_events.resize(old + (nev - ctx->ev_read));
+        CK(cudaMemcpy(ctx->host_events.data() + old, ctx->D.ev + ctx->ev_read, sizeof(ltgpu_event) * (nev - ctx->ev_read),
+                      cudaMemcpyDeviceToHost));
+        ctx->ev_read = nev;
+    }
+    // ErrorLog.txt order of the serial loop: by time step, then ascending particle id
+    std::sort(ctx->host_events.begin(), ctx->host_events.end(), [](const ltgpu_event& a, const ltgpu_event& b) {
+        return a.time != b.time ? a.time < b.time : a.particle < b.particle; });
+    int k = std::min<int>(cap, (int)ctx->host_events.size());
+    memcpy(buf, ctx->host_events.data(), sizeof(ltgpu_event) * k);
+    ctx->host_events.erase(ctx->host_events.begin(), ctx->host_events.begin() + k);
+    *n = k;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_device_ptr(ltgpu_ctx* ctx, int32_t which, void** dptr)
+{
+    if (!ctx || !dptr) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "device_ptr before set_particles");
+    LtDev& D = ctx->D;
+    switch (which) {
+    case 0: *dptr = D.x; break; case 1: *dptr = D.y; break; case 2: *dptr = D.z; break;
+    case 3: *dptr = D.age; break;
+    case 4: k_status<<<(D.n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_status); ctx->launches++; *dptr = ctx->d_status; break;
+    default: ctx->err = "device_ptr: which out of range"; return LTGPU_E_ARG;
+    }
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_timer_start(ltgpu_ctx* ctx)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->t0, ctx->compute));
+    return LTGPU_OK;
+}
+int32_t ltgpu_timer_stop(ltgpu_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return LTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->t1, ctx->compute));
+    CK(cudaEventSynchronize(ctx->t1));
+    CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return LTGPU_OK;
+}
+int64_t ltgpu_launch_count(const ltgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* ltgpu_stream(ltgpu_ctx* ctx) { return ctx ? (void*)ctx->compute : nullptr; }
+
+}  // extern "C"
