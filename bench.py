@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the LTRANS v.2b particle loop on N B200s.
+
+Workload (BASELINE.json configs[1]): Baymouth-shape synthetic grid (130x130 rho, us 20 /
+ws 21, dt 3600, idt 120), 1,000,000 passive particles per GPU with horizontal + vertical
+turbulence (Philox stream), float32 hydro fields (lossless), FP64 arithmetic.
+One bench "step" = one external time step = dt/idt = 30 internal steps of every particle
+(30 launches of the step kernel) plus the refill of one hydro record.
+
+  value : device-timed (CUDA events on the library's compute stream), inputs resident,
+          the hydro refill running on the side stream as in production.
+  e2e   : same loop through the C ABI with HOST buffers: each step pushes one hydro
+          record from host memory (H2D) and fetches x, y, z, status to host (D2H).
+  --impl reference : the CPU restatement of the reference loop (oracle/, all host
+          threads, OpenMP over particles) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B_ALG = 3624          # algorithmic bytes / particle-step, config 2
+NPART = 1_000_000
+WORKLOAD = "baymouth-shape 130x130x20 synthetic ROMS, 1M particles/GPU, HTurb+VTurb, 30 internal steps per step"
+
+
+def clocks_sampler(stop, out, gpu_index):
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [s.strip() for s in r.stdout.strip().split(",")]
+            if len(f) >= 6:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def clocks_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = [float(s[0]) for s in samples if s[0].replace(".", "").isdigit()]
+    mx = [float(s[1]) for s in samples if s[1].replace(".", "").isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": reasons, "samples": len(samples)}
+
+
+def run_reference(args):
+    """CPU arm: oracle on all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from common import World, make_params, setup
+    from oracle.oracle import Oracle
+    cores = os.cpu_count() or 1
+    n = args.cpu_particles
+    w = World()
+    prm = make_params(w, n, Behavior=0, settlementon=0, mortality=0, ErrorFlag=1, TrackCollisions=0)
+    o = Oracle()
+    setup(o, w, prm, n)
+    o.set_threads(cores)
+    stepIT = prm.dt // prm.idt
+    p = 0
+    times = []
+    for s in range(args.warmup + args.steps):
+        p += 1
+        if p > 2:
+            o.push_hydro(w.record(p)); o.rotate_hydro()
+        t = time.perf_counter()
+        o.run_external(p)
+        dt = time.perf_counter() - t
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = n * stepIT * args.steps / total
+    sample = f"{n} particles x {stepIT} internal steps per step, OpenMP over particles"
+    print(json.dumps({
+        "impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def cpu_baseline(w, n, nsteps_internal):
+    from common import make_params, setup
+    from oracle.oracle import Oracle
+    cores = os.cpu_count() or 1
+    prm = make_params(w, n, Behavior=0, settlementon=0, mortality=0, ErrorFlag=1, TrackCollisions=0)
+    o = Oracle()
+    setup(o, w, prm, n)
+    o.set_threads(cores)
+    o.step(1, 1)
+    t = time.perf_counter()
+    for it in range(2, 2 + nsteps_internal):
+        o.step(1, it)
+    dt = time.perf_counter() - t
+    o.destroy()
+    return {"value": n * nsteps_internal / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n} particles x {nsteps_internal} internal steps of the same workload, OpenMP over particles"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--particles", type=int, default=NPART, help="particles per GPU")
+    ap.add_argument("--cpu-particles", type=int, default=20000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from common import World, make_params, LtransLib
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.particles
+    w = World()
+    prm = make_params(w, n, Behavior=0, settlementon=0, mortality=0, ErrorFlag=1, TrackCollisions=0)
+    stepIT = prm.dt // prm.idt
+    g = LtransLib().create(prm, device=local)
+    g.set_grid(w.grid()); g.set_bounds(w.bounds())
+    # contiguous particle slice of the global run: ids first_id .. first_id + n - 1
+    x, y, z, dob, r, u, v = w.seed_particles(n, seed=1234 + rank)
+    g.set_particles(x, y, z, dob, None, r, u, v, first_id=1 + rank * n)
+    nrec = args.warmup + 2 * args.steps + 8
+    recs = [w.record(k) for k in range(nrec)]
+    for k in range(3):
+        g.push_hydro(recs[k])
+    h2d = sum(a.nbytes for kk, a in recs[0].items() if kk in ("zeta", "u", "v", "w", "aks"))
+    d2h = n * (3 * 8 + 4)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stats_t = torch.zeros(8, dtype=torch.int64, device="cuda")
+
+    def barrier():
+        g.sync()
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+
+    p = 0
+
+    def one_step(fetch):
+        nonlocal p
+        p += 1
+        if p > 2:
+            g.rotate_hydro()                       # record pushed during the previous step
+        if p >= 2:
+            g.push_hydro(recs[p + 1])              # prefetch next record on the copy stream
+        g.run_external(p)
+        if fetch:
+            return g.fetch(("x", "y", "z", "status"))
+
+    # p = 1, 2 run on the initial three records (no updateHydro before the 3rd external step)
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local)); th.start()
+    # ---- device-timed arm ---------------------------------------------------------
+    launches0 = g.launch_count()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)                             # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        g.timer_start()
+        one_step(False)
+        dev_ms += g.timer_stop()
+    launches = g.launch_count() - launches0
+    barrier()
+    t_dev = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_ms = float(t_dev.item())
+    # ---- end-to-end arm (host buffers in, host buffers out) ---------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = one_step(True)
+    g.sync()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_s = float(t_e.item())
+    stop.set(); th.join()
+    # settlement / statistics reduction over NVLink (north star: the only collective)
+    stats_t.copy_(torch.from_numpy(g.stats()))
+    if world_size > 1:
+        dist.all_reduce(stats_t)
+    total_steps = n * world_size * stepIT * args.steps
+    value = total_steps / (dev_ms * 1e-3)
+    e2e = total_steps / e2e_s
+    kern_ms = dev_ms / (args.steps * stepIT)                  # one k_step launch over n particles
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = B_ALG * n / (kern_ms * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "particles_per_gpu": n, "grid": "130x130 rho, us 20, ws 21",
+                       "internal_steps_per_step": stepIT, "field_storage": "f32 (lossless), [node][level][4-slot ring]",
+                       "rng": "philox4x32-10 keyed (seed; particle id, step, block)", "parallelism": f"particle slices x{world_size}",
+                       "l2": "256 MiB flush buffer written between timed steps; fields (~20 MB) are L2-resident by design"},
+            "e2e": {"value": e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_step<float>", "kernel_ms": kern_ms,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "note": "algorithmic bytes 3624 B/particle-step x particles per launch / mean launch time"},
+            "clocks": clocks_summary(samples),
+            "stats": {"settled": int(stats_t[0]), "dead": int(stats_t[1]), "out_of_bounds": int(stats_t[2]),
+                      "active": int(stats_t[6]), "events": int(stats_t[5])},
+        }
+        if not args.no_cpu and world_size == 1:
+            line["cpu_baseline"] = cpu_baseline(w, args.cpu_particles, 12)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    g.destroy()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

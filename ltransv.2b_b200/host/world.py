@@ -60,9 +60,11 @@ def s_coordinate(N, theta_s=3.0, theta_b=0.4):
 
 class World:
     def __init__(self, ni=130, nj=130, us=20, lon0=-76.2, lat0=36.9, dlon=0.004, dlat=0.0032,
-                 hmin=5.0, hmax=30.0, islands=True, open_east=True, dt_hydro=3600.0, speed=0.6):
+                 hmin=5.0, hmax=30.0, islands=True, open_east=True, dt_hydro=3600.0, speed=0.6,
+                 uniform=None):
         self.ni, self.nj, self.us, self.ws = ni, nj, us, us + 1
         self.dt_hydro, self.speed = dt_hydro, speed
+        self.uniform = uniform      # (U0, V0, K0): steady uniform flow, flat bed, zeta = 0, angle = 0
         self.proj = Projection()
         i = np.arange(ni)[None, :]
         j = np.arange(nj)[:, None]
@@ -102,6 +104,9 @@ class World:
         h = hmin + (hmax - hmin) * (0.35 + 0.45 * fi + 0.2 * np.sin(2 * np.pi * fj) * np.cos(3 * np.pi * fi))
         self.h = _f32(np.clip(h, hmin, hmax)).astype(np.float64)
         self.angle = 0.04 * np.sin(2 * np.pi * fi) * np.cos(np.pi * fj) + 0.01
+        if uniform is not None:
+            self.h = np.full((nj, ni), float(np.float32(hmax)))
+            self.angle = np.zeros((nj, ni))
         self.sc_r, self.Cs_r, self.sc_w, self.Cs_w = s_coordinate(us)
         self._grid = None
 
@@ -163,6 +168,12 @@ class World:
         (level, eta, xi) i.e. node fastest -- what one NF90_GET_VAR returns
         (hydro:1140-1364)."""
         ni, nj, us, ws = self.ni, self.nj, self.us, self.ws
+        if self.uniform is not None:
+            U0, V0, K0 = self.uniform
+            return dict(zeta=np.zeros((nj, ni), dtype), u=np.full((us, nj, ni - 1), U0, dtype),
+                        v=np.full((us, nj - 1, ni), V0, dtype), w=np.zeros((ws, nj, ni), dtype),
+                        aks=np.full((ws, nj, ni), K0, dtype), salt=np.full((us, nj, ni), 20.0, dtype),
+                        temp=np.full((us, nj, ni), 15.0, dtype))
         t = r * self.dt_hydro
         om = 2 * np.pi / 44714.0                                   # M2
         i = np.arange(ni)[None, :]; j = np.arange(nj)[:, None]
