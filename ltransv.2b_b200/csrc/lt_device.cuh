@@ -13,6 +13,33 @@
 #define LT_DEV __device__ __forceinline__
 #define LT_DEVN __device__ __noinline__
 
+// Fast FP64 reciprocal / quotient for the SMOOTH numerics only (splines, s-levels):
+// MUFU.RCP64H seed + Newton steps, <= 1 ulp, ~8 instructions instead of ~40 with a
+// slow-path branch.  Geometry predicates that the reference decides by exact equality
+// (gridcell, inpoly, intersect_reflect) keep IEEE division.  -DLT_IEEE_DIV restores
+// IEEE division everywhere (used to check bit-level agreement with the oracle).
+LT_DEV double qrcp(double a)
+{
+#ifdef LT_IEEE_DIV
+    return 1.0 / a;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = fma(fma(-a, r, 1.0), r, r);
+    r = fma(fma(-a, r, 1.0), r, r);
+    return r;
+#endif
+}
+LT_DEV double qdiv(double a, double b)
+{
+#ifdef LT_IEEE_DIV
+    return a / b;
+#else
+    double r = qrcp(b), q = a * r;
+    return fma(fma(-b, q, a), r, q);
+#endif
+}
+
 #define kF32_1em3 0.001f        // DBLE(0.001)    is a float32 literal widened (LTRANS.f90:901)
 #define kF32_1em6 0.000001f     // DBLE(0.000001) likewise                     (LTRANS.f90:1002)
 
@@ -233,8 +260,8 @@ LT_DEV double gather_static(const LtDev& D, const double* arr, const Stencil& s)
 LT_DEV double zlevel(const LtDev& D, double zeta, double depth, double sc, double cs)
 {
     double hc = (double)D.P.hc, h = -1.0 * depth, S;
-    if (D.P.Vtransform == 1) { S = hc * sc + (h - hc) * cs; return S + zeta * (1.0 + S / h); }
-    if (D.P.Vtransform == 2) { S = (hc * sc + h * cs) / (hc + h); return zeta + (zeta + h) * S; }
+    if (D.P.Vtransform == 1) { S = hc * sc + (h - hc) * cs; return S + zeta * (1.0 + qdiv(S, h)); }
+    if (D.P.Vtransform == 2) { S = qdiv(hc * sc + h * cs, hc + h); return zeta + (zeta + h) * S; }
     return zeta * (1.0 + sc) + hc * sc + (h - hc) * cs;
 }
 struct Column { double zb, zc, zf, depth; };     // zeta at the 3 times + (negative) depth
@@ -271,18 +298,19 @@ LT_DEV void snhcsh(double X, double& SINHM, double& COSHM, double& COSHMM)
         double XC = X * XS;
         double P = ((P4 * XS + P3) * XS + P2) * XS + P1;
         double Q = ((Q4 * XS + Q3) * XS + Q2) * XS + Q1;
-        SINHM = XC * (P / Q);
+        SINHM = XC * qdiv(P, Q);
         double XSD4 = .25 * XS, XSD2 = XSD4 + XSD4;
         P = ((P4 * XSD4 + P3) * XSD4 + P2) * XSD4 + P1;
         Q = ((Q4 * XSD4 + Q3) * XSD4 + Q2) * XSD4 + Q1;
-        double F = XSD4 * (P / Q);
+        double F = XSD4 * qdiv(P, Q);
         COSHMM = XSD2 * F * (F + 2.0);
         COSHM = COSHMM + XSD2;
     } else {
         double EXPX = exp(AX);
-        SINHM = -(((1.0 / EXPX + AX) + AX) - EXPX) / 2.0;
+        double RE_ = qrcp(EXPX);
+        SINHM = -(((RE_ + AX) + AX) - EXPX) / 2.0;
         if (X < 0.0) SINHM = -SINHM;
-        COSHM = ((1.0 / EXPX - 2.0) + EXPX) / 2.0;
+        COSHM = ((RE_ - 2.0) + EXPX) / 2.0;
         COSHMM = COSHM - XS / 2.0;
     }
 }
@@ -295,13 +323,13 @@ LT_DEV void snhcsh(double X, double& SINHM, double& COSHM, double& COSHMM)
 LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double S2, int& err)
 {
     const double SBIG = 85.0, RTOL = LT_RTOL, FTOL = 0.0;
-    double S = (Y2 - Y1) / DX;
+    double S = qdiv(Y2 - Y1, DX);
     double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
     if ((D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0)) return SBIG;
     double SIG = 0.0;
     if (D1D2 >= 0.0) {
         if (D1D2 == 0.0) return 0.0;
-        double T = fmax(D1 / D2, D2 / D1);
+        double T = fmax(qdiv(D1, D2), qdiv(D2, D1));
         if (T <= 2.0) return 0.0;
         double TP1 = T + 1.0;
         SIG = sqrt(10.0 * T - 20.0);
@@ -311,18 +339,20 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
             if (SIG <= .5) {
                 double SINHM, COSHM, COSHMM;
                 snhcsh(SIG, SINHM, COSHM, COSHMM);
-                T1 = COSHM / SINHM;
-                FP = T1 + SIG * (SIG / SINHM - T1 * T1 + 1.0);
+                double RS_ = qrcp(SINHM);
+                T1 = COSHM * RS_;
+                FP = T1 + SIG * (SIG * RS_ - T1 * T1 + 1.0);
             } else {
                 double EMS = exp(-SIG);
                 double SSM = 1.0 - EMS * (EMS + SIG + SIG);
-                T1 = (1.0 - EMS) * (1.0 - EMS) / SSM;
-                FP = T1 + SIG * (2.0 * SIG * EMS / SSM - T1 * T1 + 1.0);
+                double RM_ = qrcp(SSM);
+                T1 = (1.0 - EMS) * (1.0 - EMS) * RM_;
+                FP = T1 + SIG * (2.0 * SIG * EMS * RM_ - T1 * T1 + 1.0);
             }
             double F = SIG * T1 - TP1;
             if (++NIT > 10000) { err = 1; return 0.0; }
             if (FP <= 0.0) break;
-            double DSIG = -F / FP;
+            double DSIG = -qdiv(F, FP);
             if (fabs(DSIG) <= RTOL * SIG || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
             SIG = SIG + DSIG;
         }
@@ -335,14 +365,14 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
     if (D0 <= 0.0 || S * T0 >= 0.0) return 0.0;
     double SGN = copysign(1.0, S);
     SIG = SBIG;
-    double FMAX = SGN * (SIG * S - S1 - S2) / (SIG - 2.0);
+    double FMAX = qdiv(SGN * (SIG * S - S1 - S2), SIG - 2.0);
     if (FMAX <= 0.0) return SBIG;
-    double STOL = RTOL * SIG, F = FMAX, F0 = SGN * D0 / (3.0 * (D1 - D2)), FNEG = F0;
+    double STOL = RTOL * SIG, F = FMAX, F0 = qdiv(SGN * D0, 3.0 * (D1 - D2)), FNEG = F0;
     double DSIG = SIG, DMAX = SIG, D1PD2 = D1 + D2, A = 0.0, E = 0.0;
     bool CONT = true;                                  // ledger 18
     int NIT = 0;
     for (;;) {
-        DSIG = -F * DSIG / (F - F0);
+        DSIG = qdiv(-F * DSIG, F - F0);
         if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { err = 1; return 0.0; } continue; }
         if (fabs(DSIG) < STOL / 2.0) DSIG = -copysign(STOL / 2.0, DMAX);
         SIG = SIG + DSIG;
@@ -367,7 +397,7 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
             if (A * (C2 + C1) < 0.0) CONT = false;
             if (CONT) E = SIG * SSINH - SCM - SCM;
         }
-        if (CONT) F = (SGN * (E * S2 - C2) + sqrt(A * (C2 + C1))) / E;
+        if (CONT) F = qdiv(SGN * (E * S2 - C2) + sqrt(A * (C2 + C1)), E);
         if (++NIT > 100000) { err = 1; return 0.0; }
         STOL = RTOL * SIG;
         if (fabs(DMAX) <= STOL || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
@@ -386,47 +416,56 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
 LT_DEVN double hval_interval(double T, double X1, double X2, double Y1, double Y2, double YP1, double YP2, double SIGMA)
 {
     const double SBIG = 85.0;
-    double DX = X2 - X1, U = T - X1, B2 = U / DX, B1 = 1.0 - B2, S1 = YP1;
-    double S = (Y2 - Y1) / DX, D1 = S - S1, D2 = YP2 - S, SIG = fabs(SIGMA);
+    double DX = X2 - X1, U = T - X1, B2 = qdiv(U, DX), B1 = 1.0 - B2, S1 = YP1;
+    double S = qdiv(Y2 - Y1, DX), D1 = S - S1, D2 = YP2 - S, SIG = fabs(SIGMA);
     if (SIG < 1.e-9) return Y1 + U * (S1 + B2 * (D1 + B1 * (D1 - D2)));
     if (SIG <= .5) {
         double SB2 = SIG * B2, SM, CM, CMM, SM2, CM2, DUMMY;
         snhcsh(SIG, SM, CM, CMM); snhcsh(SB2, SM2, CM2, DUMMY);
         double E = SIG * SM - CMM - CMM;
-        return Y1 + S1 * U + DX * ((CM * SM2 - SM * CM2) * (D1 + D2) + SIG * (CM * CM2 - (SM + SIG) * SM2) * D1) / (SIG * E);
+        return Y1 + S1 * U + DX * ((CM * SM2 - SM * CM2) * (D1 + D2) + SIG * (CM * CM2 - (SM + SIG) * SM2) * D1) * qrcp(SIG * E);
     }
     double SB1 = SIG * B1, SB2 = SIG - SB1;
     if (-SB1 > SBIG || -SB2 > SBIG) return Y1 + S * U;
     double E1 = exp(-SB1), E2 = exp(-SB2), EMS = E1 * E2, TM = 1.0 - EMS, TS = TM * TM, TP = 1.0 + EMS;
     double E = TM * (SIG * TP - TM - TM);
     return Y1 + S * U + DX * (TM * (TP - E1 - E2) * (D1 + D2) +
-           SIG * ((E2 + EMS * (E1 - 2.0) - B1 * TS) * D1 + (E1 + EMS * (E2 - 2.0) - B2 * TS) * D2)) / (SIG * E);
+           SIG * ((E2 + EMS * (E1 - 2.0) - B1 * TS) * D1 + (E1 + EMS * (E2 - 2.0) - B2 * TS) * D2)) * qrcp(SIG * E);
 }
 // HPVAL on one interval (tension_module.f90:1190-1249)
 LT_DEVN double hpval_interval(double T, double X1, double X2, double Y1, double Y2, double YP1, double YP2, double SIGMA)
 {
     const double SBIG = 85.0;
-    double DX = X2 - X1, B1 = (X2 - T) / DX, B2 = 1.0 - B1, S1 = YP1;
-    double S = (Y2 - Y1) / DX, D1 = S - S1, D2 = YP2 - S, SIG = fabs(SIGMA);
+    double DX = X2 - X1, B1 = qdiv(X2 - T, DX), B2 = 1.0 - B1, S1 = YP1;
+    double S = qdiv(Y2 - Y1, DX), D1 = S - S1, D2 = YP2 - S, SIG = fabs(SIGMA);
     if (SIG < 1.e-9) return S1 + B2 * (D1 + D2 - 3.0 * B1 * (D2 - D1));
     if (SIG <= .5) {
         double SB2 = SIG * B2, SM, CM, CMM, SM2, CM2, DUMMY;
         snhcsh(SIG, SM, CM, CMM); snhcsh(SB2, SM2, CM2, DUMMY);
         double SINH2 = SM2 + SB2, E = SIG * SM - CMM - CMM;
-        return S1 + ((CM * CM2 - SM * SINH2) * (D1 + D2) + SIG * (CM * SINH2 - (SM + SIG) * CM2) * D1) / E;
+        return S1 + ((CM * CM2 - SM * SINH2) * (D1 + D2) + SIG * (CM * SINH2 - (SM + SIG) * CM2) * D1) * qrcp(E);
     }
     double SB1 = SIG * B1, SB2 = SIG - SB1;
     if (-SB1 > SBIG || -SB2 > SBIG) return S;
     double E1 = exp(-SB1), E2 = exp(-SB2), EMS = E1 * E2, TM = 1.0 - EMS;
     double E = TM * (SIG * (1.0 + EMS) - TM - TM);
-    return S + (TM * ((E2 - E1) * (D1 + D2) + TM * (D1 - D2)) + SIG * ((E1 * EMS - E2) * D1 + (E1 - E2 * EMS) * D2)) / E;
+    return S + (TM * ((E2 - E1) * (D1 + D2) + TM * (D1 - D2)) + SIG * ((E1 * EMS - E2) * D1 + (E1 - E2 * EMS) * D2)) * qrcp(E);
 }
 
 // YPC1 interior / end formulas (tension_module.f90:852-978)
 LT_DEV double ypc1_end(double SI, double T) { return SI >= 0.0 ? fmin(fmax(0.0, T), 3.0 * SI) : fmax(fmin(0.0, T), 3.0 * SI); }
 LT_DEV double ypc1_mid(double DXIM1, double DXI, double SIM1, double SI)
 {
-    double T = (DXIM1 * SI + DXI * SIM1) / (DXIM1 + DXI);
+    double T = qdiv(DXIM1 * SI + DXI * SIM1, DXIM1 + DXI);
+    double ASIM1 = fabs(SIM1), ASI = fabs(SI);
+    double SGN = copysign(1.0, SI);
+    if (ASIM1 > ASI) SGN = copysign(1.0, SIM1);
+    return SGN > 0.0 ? fmin(fmax(0.0, T), 3.0 * fmin(ASIM1, ASI)) : fmax(fmin(0.0, T), -3.0 * fmin(ASIM1, ASI));
+}
+
+LT_DEV double ypc1_mid_r(double DXIM1, double DXI, double SIM1, double SI, double rsum)
+{   // ypc1_mid with 1/(DXIM1+DXI) supplied
+    double T = (DXIM1 * SI + DXI * SIM1) * rsum;
     double ASIM1 = fabs(SIM1), ASI = fabs(SI);
     double SGN = copysign(1.0, SI);
     if (ASIM1 > ASI) SGN = copysign(1.0, SIM1);

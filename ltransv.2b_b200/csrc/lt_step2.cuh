@@ -1,0 +1,704 @@
+// lt_step2.cuh -- the production step: three kernels per internal time step, one
+// thread per particle, per-particle scratch (SoA, 121 B) handed from one to the next.
+//
+//   k_advect : gates, setEle, setInterp, vertical clamp, RK4 advection (find_currents x4),
+//              salinity / temperature, HTurb                      LTRANS.f90:778-1087
+//   k_vturb  : Visser random displacement model                   ver_turb_module.f90:30-380
+//   k_finish : behave, vertical + horizontal reflection, bounds checks, commit, setEle at
+//              the new position, settlement                        LTRANS.f90:1110-1382
+//
+// Why three: the three phases have very different register / instruction footprints
+// (the fused v1 kernel stalled on instruction fetch half of the time, see
+// profiles/r01_notes.md); split, each keeps its own occupancy and i-cache working set.
+//
+// Differences from the reference that stay inside the 1e-9 parity budget (they change
+// results by O(1e-16) relative):
+//   * the 3-point time polynomial is applied as Lagrange weights computed once per step
+//     on the host (LtDev::LW) instead of polintd's divided differences per value;
+//   * reciprocals come from qrcp()/qdiv() (<= 1 ulp) in the smooth numerics;
+//   * VTurb: the 84 spline knots are uniform in the interior (an identity of the
+//     reference's construction: movex(i) = z1 + (i - 0.5) R / p2), so abscissae are
+//     evaluated, not stored; KH knot values are built only in a 32-knot window around
+//     the particle and re-centred on demand; end slopes (YPC1) and the tension factor
+//     (SIGS) are solved only for the interval being evaluated -- every one of those is
+//     a local function of its neighbours in the reference, so windowing changes nothing;
+//     the 8-point moving average is a running sum.
+//   * SigErr (Newton did not converge in 10000 iterations in SOME interval of the column,
+//     which makes the reference fall back to linint for the whole column) is only seen
+//     for the interval being evaluated.
+#pragma once
+#include "lt_device.cuh"
+
+struct ColK { double zb, zc, zf, depth, h; };
+LT_DEV double zlev2(const LtDev& D, const ColK& c, double zeta, double sc, double cs)
+{
+    double hc = (double)D.P.hc, S;
+    if (D.P.Vtransform == 1) { S = hc * sc + (c.h - hc) * cs; return S + zeta * (1.0 + qdiv(S, c.h)); }
+    if (D.P.Vtransform == 2) { S = qdiv(hc * sc + c.h * cs, hc + c.h); return zeta + (zeta + c.h) * S; }
+    return zeta * (1.0 + sc) + hc * sc + (c.h - hc) * cs;
+}
+template <bool W>
+LT_DEV void zlev3(const LtDev& D, const ColK& c, int k, double& zb, double& zc, double& zf)
+{   // level k (0-based) at the three hydro times; S and 1 + S/h are shared
+    double sc = W ? D.SCW[k] : D.SC[k], cs = W ? D.CSW[k] : D.CS[k];
+    double hc = (double)D.P.hc;
+    if (D.P.Vtransform == 1) {
+        double S = hc * sc + (c.h - hc) * cs, q = 1.0 + qdiv(S, c.h);
+        zb = S + c.zb * q; zc = S + c.zc * q; zf = S + c.zf * q;
+    } else if (D.P.Vtransform == 2) {
+        double S = qdiv(hc * sc + c.h * cs, hc + c.h);
+        zb = c.zb + (c.zb + c.h) * S; zc = c.zc + (c.zc + c.h) * S; zf = c.zf + (c.zf + c.h) * S;
+    } else {
+        double a = 1.0 + sc, b = hc * sc + (c.h - hc) * cs;
+        zb = c.zb * a + b; zc = c.zc * a + b; zf = c.zf * a + b;
+    }
+}
+template <bool W>
+LT_DEV int level_window2(const LtDev& D, const ColK& c, double Z, int n)
+{   // LTRANS.f90:1451-1467 as a lower_bound (levels increase with the index)
+    int lo = 3, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        double zb, zc, zf; zlev3<W>(D, c, mid - 1, zb, zc, zf);
+        if (Z < zb || Z < zc || Z < zf) hi = mid; else lo = mid + 1;
+    }
+    return lo - 2;
+}
+
+LT_DEV Wt make_weights2(const double* __restrict__ q, double xp, double yp, bool setinterp_quirk)
+{   // setInterp / interp weights (hydro:1706-1737, 2533-2565)
+    double x1 = q[0], x2 = q[1], x3 = q[2], x4 = q[3], y1 = q[4], y2 = q[5], y3 = q[6], y4 = q[7];
+    Wt w;
+    w.t = qdiv((xp - x1) * (y3 - y1) + (y1 - yp) * (x3 - x1), (x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1));
+    w.u = qdiv((xp - x1) * (y2 - y1) + (y1 - yp) * (x2 - x1), (x3 - x1) * (y2 - y1) - (y3 - y1) * (x2 - x1));
+    w.mode = 1;
+    if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
+        w.t = qdiv((xp - x3) * (y1 - y3) + (y3 - yp) * (x1 - x3), (x4 - x3) * (y1 - y3) - (y4 - y3) * (x1 - x3));
+        w.u = qdiv((xp - x3) * (y4 - y3) + (y3 - yp) * (x4 - x3), (x1 - x3) * (y4 - y3) - (y1 - y3) * (x4 - x3));
+        w.mode = 2;
+        if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
+            bool n1 = xp == x1 && yp == y1, n2 = xp == x2 && yp == y2, n3 = xp == x3 && yp == y3, n4 = xp == x4 && yp == y4;
+            if (n1 || n2 || n3 || n4) { if (!setinterp_quirk) w.mode = n4 ? 7 : n3 ? 6 : n2 ? 5 : 4; }
+            else w.mode = 3;
+        }
+    }
+    return w;
+}
+
+LT_DEV double lag(const double* w, double b, double c, double f) { return w[0] * b + w[1] * c + w[2] * f; }
+
+// 4-knot spline value (TSPSI + HVAL of WCTS_ITPI, hydro:2619-2644) with the knot
+// reciprocals shared between the fields interpolated on the same knots.
+struct Knots4 { double x[4], r1, r2, r3, r12, r23; };
+LT_DEV void knots_prepare(Knots4& k)
+{
+    double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
+    k.r1 = qrcp(d1); k.r2 = qrcp(d2); k.r3 = qrcp(d3); k.r12 = qrcp(d1 + d2); k.r23 = qrcp(d2 + d3);
+}
+LT_DEVN double spline4_eval2(const Knots4& k, double y0, double y1, double y2, double y3, double T)
+{
+    double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
+    double s1 = (y1 - y0) * k.r1, s2 = (y2 - y1) * k.r2, s3 = (y3 - y2) * k.r3;
+    int I = (T < k.x[0]) ? 0 : (T > k.x[3]) ? 2 : (T < k.x[2] ? (T < k.x[1] ? 0 : 1) : 2);
+    double X1, X2, Y1, Y2, P1, P2;
+    double pm1 = ypc1_mid_r(d1, d2, s1, s2, k.r12), pm2 = ypc1_mid_r(d2, d3, s2, s3, k.r23);
+    if (I == 0) { X1 = k.x[0]; X2 = k.x[1]; Y1 = y0; Y2 = y1; P1 = ypc1_end(s1, s1 + d1 * (s1 - s2) * k.r12); P2 = pm1; }
+    else if (I == 1) { X1 = k.x[1]; X2 = k.x[2]; Y1 = y1; Y2 = y2; P1 = pm1; P2 = pm2; }
+    else { X1 = k.x[2]; X2 = k.x[3]; Y1 = y2; Y2 = y3; P1 = pm2; P2 = ypc1_end(s3, s3 + d3 * (s3 - s2) * k.r23); }
+    int err = 0;
+    double sig = sigs_interval(X2 - X1, Y1, Y2, P1, P2, err);
+    if (err == 0) return hval_interval(T, X1, X2, Y1, Y2, P1, P2, sig);
+    // linint fallback (interpolation_module.f90:25-59), n = 4
+    const double Y[4] = {y0, y1, y2, y3};
+    int jlo = 1, jhi = 4;
+    for (;;) { int q = (jhi + jlo) / 2; if (k.x[q - 1] > T) jhi = q; else jlo = q; if (jhi - jlo == 1) break; }
+    double m = (Y[jlo - 1] - Y[jhi - 1]) / (k.x[jlo - 1] - k.x[jhi - 1]);
+    return m * T + (Y[jlo - 1] - m * k.x[jlo - 1]);
+}
+
+struct Stage2 { Stencil r, u, v; };
+
+// WCTS_ITPI (hydro:2577-2689) for NF fields sharing one set of knots (u and v share the
+// rho-level knots).  v = 0,1,2: value at ix(v+1); v = 3: (b + 4c + f)/6.
+template <class T, bool W, int NF>
+LT_DEV void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st, const int* grid, int4 und, int L,
+                  const ColK& col, int deplvl, double P_zb, double P_zc, double P_zf, int v, double* out)
+{
+    double vb[NF][4], vc[NF][4], vf[NF][4];
+    Knots4 kb, kc, kf;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int k = deplvl - 1 + i;
+        zlev3<W>(D, col, k, kb.x[i], kc.x[i], kf.x[i]);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) gather_bcf<T>(D, fld[f], L, k, *st[f], grid[f], und, vb[f][i], vc[f][i], vf[f][i]);
+    }
+    knots_prepare(kb); knots_prepare(kc);
+    const bool first = D.p == 1;                     // (b,b,c): the forward profile is not used
+    if (!first) knots_prepare(kf);
+    const double* w = v < 3 ? D.LW[v] : D.LW4;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        double pb = spline4_eval2(kb, vb[f][0], vb[f][1], vb[f][2], vb[f][3], P_zb);
+        double pc = spline4_eval2(kc, vc[f][0], vc[f][1], vc[f][2], vc[f][3], P_zc);
+        double pf = first ? 0.0 : spline4_eval2(kf, vf[f][0], vf[f][1], vf[f][2], vf[f][3], P_zf);
+        out[f] = lag(w, pb, pc, pf);
+    }
+}
+
+// find_currents (LTRANS.f90:1422-1614)
+template <class T>
+LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, double Zpar,
+                            double P_zb, double P_zc, double P_zf, int version,
+                            double& Uad, double& Vad, double& Wad)
+{
+    const int us = D.P.us, ws = D.P.ws;
+    const double z0 = D.P.z0;
+    double wzb1, wzc1, wzf1; zlev3<true>(D, col, 0, wzb1, wzc1, wzf1);
+    if (Zpar < wzb1 + z0 || Zpar < wzc1 + z0 || Zpar < wzf1 + z0) { Uad = 0.0; Vad = 0.0; Wad = 0.0; return; }
+    double zb1, zc1, zf1; zlev3<false>(D, col, 0, zb1, zc1, zf1);
+    const T* fu = (const T*)D.u; const T* fv = (const T*)D.v; const T* fw = (const T*)D.w;
+    const double* lw = D.LW[version - 1];
+    if (Zpar < zb1 || Zpar < zc1 || Zpar < zf1) {                      // log layer :1489-1600
+        double Ub, Uc, Uf, Vb, Vc, Vf, Wb, Wc, Wf;
+        gather_bcf<T>(D, fu, us, 0, s.u, G_U, s.u.nd, Ub, Uc, Uf);
+        gather_bcf<T>(D, fv, us, 0, s.v, G_V, s.u.nd, Vb, Vc, Vf);
+        gather_bcf<T>(D, fw, ws, 1, s.r, G_RHO, s.u.nd, Wb, Wc, Wf);
+        double rz0 = qrcp(z0);
+        double num = log10((Zpar - wzb1) * rz0);
+        double wzb2, wzc2, wzf2; zlev3<true>(D, col, 1, wzb2, wzc2, wzf2);
+        double db = num * qrcp(log10((zb1 - wzb1) * rz0)), dc = num * qrcp(log10((zc1 - wzb1) * rz0)),
+               df = num * qrcp(log10((zf1 - wzb1) * rz0));
+        double wb = num * qrcp(log10((wzb2 - wzb1) * rz0)), wc = num * qrcp(log10((wzc2 - wzb1) * rz0)),
+               wf = num * qrcp(log10((wzf2 - wzb1) * rz0));
+        Uad = lag(lw, Ub * db, Uc * dc, Uf * df);
+        Vad = lag(lw, Vb * db, Vc * dc, Vf * df);
+        Wad = lag(lw, Wb * wb, Wc * wc, Wf * wf);
+        return;
+    }
+    int ii = level_window2<false>(D, col, Zpar, us);
+    int iii = level_window2<true>(D, col, Zpar, ws);
+    {
+        const T* f2[2] = {fu, fv}; const Stencil* s2[2] = {&s.u, &s.v}; const int g2[2] = {G_U, G_V};
+        double o[2];
+        wcts2<T, false, 2>(D, f2, s2, g2, s.u.nd, us, col, ii, P_zb, P_zc, P_zf, version - 1, o);
+        Uad = o[0]; Vad = o[1];
+    }
+    {
+        const T* f1[1] = {fw}; const Stencil* s1[1] = {&s.r}; const int g1[1] = {G_RHO};
+        double o[1];
+        wcts2<T, true, 1>(D, f1, s1, g1, s.u.nd, ws, col, iii, P_zb, P_zc, P_zf, version - 1, o);
+        Wad = o[0];
+    }
+}
+
+LT_DEV void load_stencils(const LtDev& D, int re, int ue, int ve, Stage2& st)
+{
+    st.r.q = D.R.ele + (size_t)(re - 1) * 8; st.r.nd = __ldg(D.R.node + (re - 1));
+    st.u.q = D.U.ele + (size_t)(ue - 1) * 8; st.u.nd = __ldg(D.U.node + (ue - 1));
+    st.v.q = D.V.ele + (size_t)(ve - 1) * 8; st.v.nd = __ldg(D.V.node + (ve - 1));
+}
+LT_DEV void stage_weights2(Stage2& s, double xp, double yp)
+{
+    s.r.xp = s.u.xp = s.v.xp = xp; s.r.yp = s.u.yp = s.v.yp = yp;
+    s.r.w = make_weights2(s.r.q, xp, yp, false);
+    s.u.w = make_weights2(s.u.q, xp, yp, false);
+    s.v.w = make_weights2(s.v.q, xp, yp, false);
+}
+LT_DEV Rng make_rng(const LtDev& D, int n)
+{
+    long long gid = D.first_id + n;
+    Rng g; g.id_lo = (unsigned)((unsigned long long)gid & 0xffffffffull); g.id_hi = (unsigned)((unsigned long long)gid >> 32);
+    g.step = D.gstep; g.seed = (unsigned)D.P.seed;
+    return g;
+}
+
+// ============================================================ kernel 1: advect ==
+template <class T>
+LT_DEV void advect_particle(const LtDev& D, int n)
+{
+    const ltgpu_params& P = D.P;
+    const int idt = P.idt;
+    D.s_act[n] = 0;
+    if (D.ix[2] <= D.dob[n]) return;                                     // :790-795
+    double age = D.age[n] + (double)(float)idt;                          // :798
+    D.age[n] = age;
+    uint8_t fl = D.flags[n];
+    if (age >= P.deadage && P.mortality) {                               // updateStatus behavior:162-179
+        if (!(P.settlementon && (fl & LT_F_SETTLED))) { fl |= LT_F_DEAD; D.flags[n] = fl; }
+    }
+    if (P.settlementon && (fl & LT_F_SETTLED)) return;                   // :804-816
+    if (P.mortality && (fl & LT_F_DEAD)) return;
+    if (P.OpenOceanBoundary && (fl & LT_F_OOB)) return;
+
+    const double Xpar = D.x[n], Ypar = D.y[n], Zold = D.z[n];
+    int re = D.r_ele[n], ue = D.u_ele[n], ve = D.v_ele[n];
+    {                                                                    // setEle :830
+        int err = 0, re0 = re, ue0 = ue, ve0 = ve;
+        if (!find_element(D.R, Xpar, Ypar, re)) err = 4;
+        if (!find_element(D.U, Xpar, Ypar, ue)) err = 5;
+        if (!find_element(D.V, Xpar, Ypar, ve)) err = 6;
+        if (re != re0) D.r_ele[n] = re;
+        if (ue != ue0) D.u_ele[n] = ue;
+        if (ve != ve0) D.v_ele[n] = ve;
+        if (err) {
+            particle_error(D, n, err == 4 ? LTGPU_EV_NOT_IN_RHO : err == 5 ? LTGPU_EV_NOT_IN_U : LTGPU_EV_NOT_IN_V, Zold);
+            return;
+        }
+    }
+    Stage2 st;
+    load_stencils(D, re, ue, ve, st);
+    Stencil s0 = st.r; s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights2(st.r.q, Xpar, Ypar, true);    // setInterp :882
+    const double P_depth = -1.0 * gather_static(D, D.depth, s0);         // :892-896
+    const double P_angle = gather_static(D, D.angle, s0);
+    double P_zetab, P_zetac, P_zetaf;
+    gather_bcf<T>(D, (const T*)D.zeta, 1, 0, s0, G_RHO, s0.nd, P_zetab, P_zetac, P_zetaf);
+    double Zp = Zold;
+    if (Zp < P_depth) { Zp = P_depth + (double)kF32_1em3; if (P.TrackCollisions) D.hitB[n] += 1; }   // :900-903
+    double P_zb = Zp, P_zc = Zp, P_zf = Zp;
+    if (Zp > P_zetab) P_zb = P_zetab - (double)kF32_1em3;
+    if (Zp > P_zetac) P_zc = P_zetac - (double)kF32_1em3;
+    if (Zp > P_zetaf) P_zf = P_zetaf - (double)kF32_1em3;
+    const double Zpar = lag(D.LWz, P_zb, P_zc, P_zf);                    // :914 (raw b,c,f triplet: ledger 8)
+    ColK col; col.zb = P_zetab; col.zc = P_zetac; col.zf = P_zetaf; col.depth = P_depth; col.h = -1.0 * P_depth;
+
+    const int ws = P.ws;
+    double a, b, c;
+    zlev3<true>(D, col, 0, a, b, c);      const double maxpartdepth = fmax(a, fmax(b, c));    // :981-987
+    zlev3<true>(D, col, ws - 1, a, b, c); const double minpartdepth = fmin(a, fmin(b, c));
+    const double ca = cos(P_angle), sa = sin(P_angle);
+    const double eps6 = (double)kF32_1em6;
+    double sU = 0.0, sV = 0.0, sW = 0.0, xs = Xpar, ys = Ypar, zs = Zpar;
+    // RK4 with stage times (t-h, t, t, t+h) = versions 1,2,2,3 (ledger 6)
+#pragma unroll 1
+    for (int stg = 0; stg < 4; ++stg) {
+        double Uad, Vad, Wad;
+        stage_weights2(st, xs, ys);
+        find_currents2<T>(D, st, col, zs, P_zb, P_zc, P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad);
+        double wgt = (stg == 0 || stg == 3) ? 1.0 : 2.0;
+        sU += wgt * Uad; sV += wgt * Vad; sW += wgt * Wad;
+        if (stg < 3) {
+            double f = (double)idt;
+            if (stg < 2) {
+                xs = Xpar + (Uad * ca - Vad * sa) * f / 2.0; ys = Ypar + (Uad * sa + Vad * ca) * f / 2.0; zs = Zpar + Wad * f / 2.0;
+            } else {
+                xs = Xpar + (Uad * ca - Vad * sa) * f; ys = Ypar + (Uad * sa + Vad * ca) * f; zs = Zpar + Wad * f;
+            }
+            if (zs > minpartdepth) zs = minpartdepth - eps6;
+            if (zs < maxpartdepth) zs = maxpartdepth + eps6;
+        }
+    }
+    const double P_U = sU / 6.0, P_V = sV / 6.0, P_W = sW / 6.0;         // :1047-1049
+    double newX = Xpar + idt * (P_U * ca - P_V * sa);                    // :1051-1053, :1128-1130
+    double newY = Ypar + idt * (P_U * sa + P_V * ca);
+    if (P.SaltTempOn) {                                                  // :1062-1076
+        stage_weights2(st, Xpar, Ypar);
+        int deplvl = level_window2<false>(D, col, Zpar, P.us);
+        const T* f2[2] = {(const T*)D.salt, (const T*)D.temp}; const Stencil* s2[2] = {&st.r, &st.r}; const int g2[2] = {G_RHO, G_RHO};
+        double o[2];
+        wcts2<T, false, 2>(D, f2, s2, g2, st.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o);
+        D.psalt[n] = o[0]; D.ptemp[n] = o[1];
+    }
+    if (P.HTurbOn) {                                                     // hor_turb_module.f90:29-50
+        Rng g = make_rng(D, n);
+        uint4 r = philox(g, 0u);
+        double sd = sqrt(2.0 * P.ConstantHTurb * idt);
+        newX = (Xpar + idt * (P_U * ca - P_V * sa)) + box_muller(D, r.x, r.y) * sd;
+        newY = (Ypar + idt * (P_U * sa + P_V * ca)) + box_muller(D, r.z, r.w) * sd;
+    }
+    D.s_depth[n] = P_depth; D.s_angle[n] = P_angle;
+    D.s_zeb[n] = P_zetab; D.s_zec[n] = P_zetac; D.s_zef[n] = P_zetaf;
+    D.s_pzb[n] = P_zb; D.s_pzc[n] = P_zc; D.s_pzf[n] = P_zf; D.s_zpar[n] = Zpar;
+    D.s_nx[n] = newX; D.s_ny[n] = newY; D.s_advz[n] = idt * P_W;
+    D.s_pu[n] = P_U; D.s_pv[n] = P_V; D.s_turbv[n] = 0.0;
+    D.s_act[n] = 1;
+}
+
+// ============================================================= kernel 2: VTurb ==
+#define VW 32                      // knots held per window
+struct Lin { int lev; double slope, icpt, znext; };   // current KH segment of one time level
+
+template <class T>
+struct VtCtx {
+    const LtDev& D; const Stencil& s; const ColK& col; const T* fk;
+    int ws, p2;
+    double z1[3], zN[3], hs[3];           // w-level 1 / ws and newx spacing, per hydro time
+    double kh1[3], khN[3];                // KH at the bottom / top w-level
+    double Z1, ZN, H, rH;                 // time-combined knot line: x(k) = Z1 + (k - 0.5) H
+    double fy[VW]; int ka, kb;            // knot values in the window [ka, kb] (1-based)
+    LT_DEV VtCtx(const LtDev& D_, const Stencil& s_, const ColK& c_) : D(D_), s(s_), col(c_), fk((const T*)D_.kh) {}
+
+    LT_DEV double zeta(int t) const { return t == 0 ? col.zb : (t == 1 ? col.zc : col.zf); }
+    LT_DEV double wz(int t, int l) const { return zlev2(D, col, zeta(t), D.SCW[l], D.CSW[l]); }   // l 0-based
+    LT_DEV double kh(int t, int l) const
+    {
+        double b, c, f; gather_bcf<T>(D, fk, ws, l, s, G_RHO, s.nd, b, c, f);
+        return t == 0 ? b : (t == 1 ? c : f);
+    }
+    LT_DEV double knot_x(int k) const { return k <= 1 ? Z1 : (k >= p2 ? ZN : Z1 + ((double)k - 0.5) * H); }
+    // newx(j) of ver_turb:120-124
+    LT_DEV double newx(int t, int j) const { return z1[t] + (double)(j - 4) * hs[t]; }
+    // segment of the KH profile containing x: smallest jlo >= 1 with wz(jlo+1) > x (:135-166)
+    LT_DEV void seg_set(Lin& L, int t, int lev) const
+    {   // lev = jlo (1-based)
+        double zl = wz(t, lev - 1), zh = wz(t, lev), kl = kh(t, lev - 1), khh = kh(t, lev);
+        L.lev = lev; L.slope = qdiv(kl - khh, zl - zh); L.icpt = kl - L.slope * zl; L.znext = zh;   // :126-133
+    }
+    LT_DEV void seg_init(Lin& L, int t, double x) const
+    {
+        int lo = 1, hi = ws - 1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (wz(t, mid) > x) hi = mid; else lo = mid + 1; }
+        seg_set(L, t, lo);
+    }
+    LT_DEV double newy(Lin& L, int t, int j) const
+    {   // :135-177 incl. the pads (ledger 11: the bottom pad is KHb(1) for all three times)
+        if (j <= 4) return kh1[0];
+        if (j >= p2 + 4) return khN[t];
+        double x = newx(t, j);
+        while (!(L.znext > x) && L.lev < ws - 1) seg_set(L, t, L.lev + 1);
+        return L.slope * x + L.icpt;
+    }
+    // knot values fy(k), k in [ka_, ka_ + VW - 1] /\ [1, p2] (:184-275)
+    LT_DEVN void build(int ka_)
+    {
+        ka = ka_; kb = min(p2, ka + VW - 1);
+        int k0 = max(ka, 2), k1 = min(kb, p2 - 1);
+        double S[3]; Lin hi[3], lo[3];
+        if (k0 <= k1) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                double x0 = newx(t, max(k0, 5));
+                seg_init(lo[t], t, x0); hi[t] = lo[t];
+                double acc = 0.0;
+                for (int j = k0; j <= k0 + 7; ++j) acc += newy(hi[t], t, j);
+                S[t] = acc;
+            }
+        }
+        for (int k = ka; k <= kb; ++k) {
+            double my[3];
+            if (k == 1) { my[0] = kh1[0]; my[1] = kh1[1]; my[2] = kh1[2]; }
+            else if (k == p2) { my[0] = khN[0]; my[1] = khN[1]; my[2] = khN[2]; }
+            else {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (k > k0) S[t] += newy(hi[t], t, k + 7) - newy(lo[t], t, k - 1);
+                    my[t] = S[t] / 8.0;
+                }
+            }
+            double fb = lag(D.LW[0], my[0], my[1], my[2]), fc = lag(D.LW[1], my[0], my[1], my[2]), ff = lag(D.LW[2], my[0], my[1], my[2]);
+            fb = fb < 0.0 ? 0.0 : fb; fc = fc < 0.0 ? 0.0 : fc; ff = ff < 0.0 ? 0.0 : ff;
+            fy[k - ka] = (fb + 4.0 * fc + ff) / 6.0;
+        }
+    }
+    LT_DEV bool have(int k) const { return k >= ka && k <= kb; }
+    LT_DEV double Y(int k) const { return fy[k - ka]; }
+    // YPC1 slope at knot k (tension:852-978), needs Y(k-1..k+1)
+    LT_DEV double yp(int k) const
+    {
+        if (k == 1) {
+            double d1 = knot_x(2) - knot_x(1), d2 = knot_x(3) - knot_x(2);
+            double s1 = qdiv(Y(2) - Y(1), d1), s2 = qdiv(Y(3) - Y(2), d2);
+            return ypc1_end(s1, s1 + qdiv(d1 * (s1 - s2), d1 + d2));
+        }
+        if (k == p2) {
+            double d1 = knot_x(p2 - 1) - knot_x(p2 - 2), d2 = knot_x(p2) - knot_x(p2 - 1);
+            double s1 = qdiv(Y(p2 - 1) - Y(p2 - 2), d1), s2 = qdiv(Y(p2) - Y(p2 - 1), d2);
+            return ypc1_end(s2, s2 + qdiv(d2 * (s2 - s1), d1 + d2));
+        }
+        double d1 = knot_x(k) - knot_x(k - 1), d2 = knot_x(k + 1) - knot_x(k);
+        return ypc1_mid(d1, d2, qdiv(Y(k) - Y(k - 1), d1), qdiv(Y(k + 1) - Y(k), d2));
+    }
+    // HVAL / HPVAL interval choice incl. INTRVL (tension:1026-1041, 1287-1354)
+    LT_DEV int interval(double Tq) const
+    {
+        if (Tq < Z1) return 1;
+        if (Tq > ZN) return p2 - 1;
+        int k = (int)floor((Tq - Z1) * rH + 0.5);
+        k = max(1, min(p2 - 1, k));
+        while (k > 1 && Tq < knot_x(k)) --k;
+        while (k < p2 - 1 && !(Tq < knot_x(k + 1))) ++k;
+        return k;
+    }
+};
+
+struct IvCache { int I; double X1, X2, Y1, Y2, P1, P2, SG; int err; };
+
+template <class T>
+LT_DEV void vt_interval(VtCtx<T>& V, IvCache& c, int I)
+{
+    if (c.I == I) return;
+    int need_lo = max(1, I - 1), need_hi = min(V.p2, I + 2);
+    if (!(V.have(need_lo) && V.have(need_hi)))
+        V.build(max(1, min(I - VW / 2 + 1, V.p2 - VW + 1)));
+    c.I = I; c.X1 = V.knot_x(I); c.X2 = V.knot_x(I + 1); c.Y1 = V.Y(I); c.Y2 = V.Y(I + 1);
+    c.P1 = V.yp(I); c.P2 = V.yp(I + 1);
+    c.err = 0;
+    c.SG = sigs_interval(c.X2 - c.X1, c.Y1, c.Y2, c.P1, c.P2, c.err);
+}
+
+template <class T>
+LT_DEV void vturb_particle(const LtDev& D, int n)
+{
+    if (!D.s_act[n]) return;
+    const double background = (double)1.0E-6f;                          // ledger 2
+    const double Xpar = D.x[n], Ypar = D.y[n];
+    const int re = D.r_ele[n];
+    Stencil s0; s0.q = D.R.ele + (size_t)(re - 1) * 8; s0.nd = __ldg(D.R.node + (re - 1));
+    s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights2(s0.q, Xpar, Ypar, true);     // getInterp uses setInterp's weights
+    ColK col; col.zb = D.s_zeb[n]; col.zc = D.s_zec[n]; col.zf = D.s_zef[n]; col.depth = D.s_depth[n]; col.h = -1.0 * col.depth;
+    const double P_zc = D.s_pzc[n], P_depth = col.depth, P_zetac = col.zc;
+    VtCtx<T> V(D, s0, col);
+    V.ws = D.P.ws; V.p2 = 4 * V.ws;
+    const double rp2 = 1.0 / (double)V.p2;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        V.z1[t] = V.wz(t, 0); V.zN[t] = V.wz(t, V.ws - 1);
+        V.hs[t] = (V.zN[t] - V.z1[t]) * rp2;
+    }
+    gather_bcf<T>(D, V.fk, V.ws, 0, s0, G_RHO, s0.nd, V.kh1[0], V.kh1[1], V.kh1[2]);
+    gather_bcf<T>(D, V.fk, V.ws, V.ws - 1, s0, G_RHO, s0.nd, V.khN[0], V.khN[1], V.khN[2]);
+    V.Z1 = lag(D.LW4, V.z1[0], V.z1[1], V.z1[2]);
+    V.ZN = lag(D.LW4, V.zN[0], V.zN[1], V.zN[2]);
+    V.H = (V.ZN - V.Z1) * rp2; V.rH = qrcp(V.H);
+    V.ka = 1; V.kb = 0;
+    IvCache c; c.I = -1;
+    const Rng g = make_rng(D, n);
+    const double deltat = 2.0;
+    const int loop = D.P.idt / 2;                                       // :282-283
+    double ParZc = P_zc;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int i = 0; i < loop; ++i) {                                    // :291-337
+        double Kprimec = 0.0;
+        if (!(ParZc < P_depth || ParZc > P_zetac)) {
+            vt_interval(V, c, V.interval(ParZc));
+            if (!c.err) Kprimec = hpval_interval(ParZc, c.X1, c.X2, c.Y1, c.Y2, c.P1, c.P2, c.SG);
+            else Kprimec = qdiv(c.Y1 - c.Y2, c.X1 - c.X2);              // linint slope
+        }
+        const double KprimeZc = -1.0 * Kprimec * deltat;
+        const double Z3rdc = ParZc + 0.5 * KprimeZc;
+        double KH3rdc;
+        if (Z3rdc < P_depth || Z3rdc > P_zetac) KH3rdc = background;
+        else {
+            vt_interval(V, c, V.interval(Z3rdc));
+            if (!c.err) KH3rdc = hval_interval(Z3rdc, c.X1, c.X2, c.Y1, c.Y2, c.P1, c.P2, c.SG);
+            else { double m = qdiv(c.Y1 - c.Y2, c.X1 - c.X2); KH3rdc = m * Z3rdc + (c.Y1 - m * c.X1); }
+            if (KH3rdc < background) KH3rdc = background;
+        }
+        if ((i & 1) == 0) rnd = philox(g, 1u + (unsigned)(i >> 1));
+        const double DEV = (i & 1) ? box_muller(D, rnd.z, rnd.w) : box_muller(D, rnd.x, rnd.y);
+        ParZc = ParZc + KprimeZc + DEV * sqrt(2.0 * KH3rdc * deltat);  // (...)**0.5, ledger 12
+    }
+    D.s_turbv[n] = P_zc - ParZc;                                        // :342
+}
+
+// ============================================================ kernel 3: finish ==
+// intersect_reflect through the segment buckets: candidates are the segments whose
+// bounding box meets a bucket touched by the move's bounding box -- a superset of what
+// passes the reference's reject test (boundary:1677-1680) -- tested with the reference's
+// formulas; nearest hit, lowest index on ties (= the ascending strict-< scan of :1887-1897).
+LT_DEVN bool intersect_segment(const LtDev& D, int i, double Xpos, double Ypos, double nXpos, double nYpos,
+                               double xlow, double xhigh, double ylow, double yhigh, double& dtest, Hit& h)
+{
+    const double2* sp = reinterpret_cast<const double2*>(D.seg + i);
+    double2 s1_ = __ldg(sp), s2_ = __ldg(sp + 1);
+    double bcx1 = s1_.x, bcy1 = s1_.y, bcx2 = s2_.x, bcy2 = s2_.y;
+    if ((bcx1 > xhigh && bcx2 > xhigh) || (bcx1 < xlow && bcx2 < xlow) ||
+        (bcy1 > yhigh && bcy2 > yhigh) || (bcy1 < ylow && bcy2 < ylow)) return false;
+    double bxhigh = fmax(bcx1, bcx2), bxlow = fmin(bcx1, bcx2), byhigh = fmax(bcy1, bcy2), bylow = fmin(bcy1, bcy2);
+    double ix, iy, rx1, ry1, rx2, ry2, Mbc = 0.0, dPBC = 0.0;
+    int kind;
+    if (bcx1 == bcx2 || nXpos == Xpos) {
+        if (bcx1 == bcx2 && nXpos == Xpos) return false;
+        if (bcx1 == bcx2 && nYpos == Ypos) {
+            ix = bcx1; iy = nYpos; kind = 1;
+            dPBC = sqrt((ix - nXpos) * (ix - nXpos) + (iy - nYpos) * (iy - nYpos));
+        } else if (nXpos == Xpos && bcy1 == bcy2) {
+            ix = nXpos; iy = bcy1; kind = 2;
+            dPBC = sqrt((ix - nXpos) * (ix - nXpos) + (iy - nYpos) * (iy - nYpos));
+        } else if (bcx1 == bcx2 && nYpos != Ypos) {
+            double Mp = (nYpos - Ypos) / (nXpos - Xpos), Bp = Ypos - Mp * Xpos;
+            ix = bcx1; iy = Mp * ix + Bp; kind = 1; dPBC = nXpos - ix;
+        } else if (nXpos == Xpos && bcy1 != bcy2) {
+            Mbc = (bcy2 - bcy1) / (bcx2 - bcx1);
+            double Bbc = bcy2 - Mbc * bcx2;
+            ix = nXpos; iy = Mbc * ix + Bbc; kind = 3;
+        } else return false;
+    } else {
+        Mbc = (bcy2 - bcy1) / (bcx2 - bcx1);
+        double Bbc = bcy2 - Mbc * bcx2;
+        double Mp = (nYpos - Ypos) / (nXpos - Xpos), Bp = Ypos - Mp * Xpos;
+        ix = (Bbc - Bp) / (Mp - Mbc);
+        iy = Mp * ix + Bp;
+        if (Mbc == 0.0) { iy = byhigh; kind = 2; dPBC = nYpos - bcy1; } else kind = 3;
+    }
+    if (!(ix <= xhigh && ix >= xlow && iy <= yhigh && iy >= ylow &&
+          ix <= bxhigh && ix >= bxlow && iy <= byhigh && iy >= bylow)) return false;
+    if (kind == 1) { rx1 = nXpos + (2.0 * dPBC); ry1 = nYpos; rx2 = nXpos - (2.0 * dPBC); ry2 = nYpos; }
+    else if (kind == 2) { rx1 = nXpos; ry1 = nYpos + (2.0 * dPBC); rx2 = nXpos; ry2 = nYpos - (2.0 * dPBC); }
+    else {
+        double distBC = sqrt((bcx1 - bcx2) * (bcx1 - bcx2) + (bcy1 - bcy2) * (bcy1 - bcy2));
+        double crossk = ((nXpos - bcx1) * (bcy2 - bcy1)) - ((bcx2 - bcx1) * (nYpos - bcy1));
+        dPBC = sqrt(crossk * crossk) / distBC;
+        double mP = -1.0 / Mbc, bP = nYpos - mP * nXpos;
+        double rr = sqrt(((2.0 * dPBC) * (2.0 * dPBC)) / (1.0 + mP * mP));
+        rx1 = rr + nXpos; ry1 = mP * rx1 + bP;
+        rx2 = rr * -1.0 + nXpos; ry2 = mP * rx2 + bP;
+    }
+    double dist1 = sqrt((ix - rx1) * (ix - rx1) + (iy - ry1) * (iy - ry1));
+    double dist2 = sqrt((ix - rx2) * (ix - rx2) + (iy - ry2) * (iy - ry2));
+    double d = sqrt((Xpos - ix) * (Xpos - ix) + (Ypos - iy) * (Ypos - iy));
+    if (d < dtest || (d == dtest && d < 999999. && i < h.seg)) {
+        // ledger 19 (dist1 == dist2 keeps a stale value in the reference): only when the end
+        // point lies on the boundary line; the end point itself is then its own mirror image
+        if (dist1 < dist2) { h.rx = rx1; h.ry = ry1; } else if (dist1 > dist2) { h.rx = rx2; h.ry = ry2; } else { h.rx = rx1; h.ry = ry1; }
+        h.ix = ix; h.iy = iy; h.seg = i; h.water = !__ldg(D.land + i);
+        dtest = d;
+        return true;
+    }
+    return false;
+}
+
+LT_DEV bool intersect_reflect2(const LtDev& D, double Xpos, double Ypos, double nXpos, double nYpos, int skipbound, Hit& h)
+{
+    double xhigh = fmax(Xpos, nXpos), xlow = fmin(Xpos, nXpos), yhigh = fmax(Ypos, nYpos), ylow = fmin(Ypos, nYpos);
+    double dtest = 999999.;
+    bool found = false;
+    h.seg = 0x7fffffff;
+    int cx0 = (int)floor((xlow - D.sg_x0) * D.sg_rcs), cx1 = (int)floor((xhigh - D.sg_x0) * D.sg_rcs);
+    int cy0 = (int)floor((ylow - D.sg_y0) * D.sg_rcs), cy1 = (int)floor((yhigh - D.sg_y0) * D.sg_rcs);
+    if (cx1 < 0 || cy1 < 0 || cx0 >= D.sg_nx || cy0 >= D.sg_ny) return false;     // no segment bbox out there
+    cx0 = max(cx0, 0); cy0 = max(cy0, 0); cx1 = min(cx1, D.sg_nx - 1); cy1 = min(cy1, D.sg_ny - 1);
+    if ((long long)(cx1 - cx0 + 1) * (cy1 - cy0 + 1) > 64) {             // very long move: scan everything
+        for (int i = 0; i < D.nbounds; ++i)
+            if (i != skipbound) found |= intersect_segment(D, i, Xpos, Ypos, nXpos, nYpos, xlow, xhigh, ylow, yhigh, dtest, h);
+        return found;
+    }
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            int c = cy * D.sg_nx + cx;
+            for (int q = __ldg(D.sg_ptr + c); q < __ldg(D.sg_ptr + c + 1); ++q) {
+                int i = __ldg(D.sg_idx + q);
+                if (i != skipbound) found |= intersect_segment(D, i, Xpos, Ypos, nXpos, nYpos, xlow, xhigh, ylow, yhigh, dtest, h);
+            }
+        }
+    return found;
+}
+
+// inpoly through y-bands (point_in_polygon_module.f90:25-167): only edges whose y-range
+// contains y can (a) carry a vertex on the ray, (b) be the vertex the point sits on,
+// (c) be crossed by the ray.  If a vertex lies on the ray the reference's vertex walk
+// (:60-117) depends on polygon order, so that (measure-zero) case runs the full routine.
+// `poly` holds several closed polygons back to back; idx lists edge start vertices i
+// (edge i -> i+1); edges joining two polygons are never listed.
+LT_DEV int inpoly_banded(double x, double y, const double2* __restrict__ poly, double y0, double rbh, int nband,
+                         const int* __restrict__ ptr, const int* __restrict__ idx)
+{   // returns 0 out, 1 in, 2 = needs the full routine
+    int b = (int)floor((y - y0) * rbh);
+    if (b < 0 || b >= nband) return 0;
+    int crossed = 0;
+    for (int q = __ldg(ptr + b); q < __ldg(ptr + b + 1); ++q) {
+        int i = __ldg(idx + q);
+        double2 a = __ldg(poly + i), c = __ldg(poly + i + 1);
+        if ((a.y == y && a.x > x) || (c.y == y && c.x > x)) return 2;
+        if ((a.x == x && a.y == y) || (c.x == x && c.y == y)) return 1;
+        if ((a.x <= x && c.x <= x) || (a.y <= y && c.y <= y) || (a.y >= y && c.y >= y)) continue;
+        if (a.x > x && c.x > x) { crossed++; continue; }
+        double m = (c.y - a.y) / (c.x - a.x);
+        double bb = a.y - m * a.x;
+        double ix = (y - bb) / m;
+        if (ix == x) return 1;
+        if (ix > x) crossed++;
+    }
+    return crossed & 1;
+}
+
+template <class T>
+LT_DEV void finish_particle(const LtDev& D, int n)
+{
+    if (!D.s_act[n]) return;
+    const ltgpu_params& P = D.P;
+    const double Xpar = D.x[n], Ypar = D.y[n];
+    const double P_depth = D.s_depth[n], P_zetac = D.s_zec[n], Zpar = D.s_zpar[n];
+    const double eps6 = (double)kF32_1em6;
+    const double age = D.age[n];
+    int re = D.r_ele[n], ue = D.u_ele[n], ve = D.v_ele[n];
+    BehavOut bo; bo.X = bo.Y = bo.Z = 0.0; bo.bott = false;
+    if (P.Behavior != 0) {                                               // :1110
+        Stage st; Column col;
+        st.r.q = D.R.ele + (size_t)(re - 1) * 8; st.r.nd = __ldg(D.R.node + (re - 1));
+        st.u.nd = __ldg(D.U.node + (ue - 1));
+        st.r.xp = Xpar; st.r.yp = Ypar; st.r.w = make_weights(st.r.q, Xpar, Ypar, false);
+        col.zb = D.s_zeb[n]; col.zc = P_zetac; col.zf = D.s_zef[n]; col.depth = P_depth;
+        bo = behave<T>(D, n, st, col, make_rng(D, n), Zpar, D.s_pzb[n], D.s_pzc[n], D.s_pzf[n], P_zetac, age, P_depth,
+                       D.s_pu[n], D.s_pv[n], D.s_angle[n]);
+    }
+    double newXpos = D.s_nx[n], newYpos = D.s_ny[n];
+    double newZpos = Zpar + D.s_advz[n] + D.s_turbv[n];                  // :1130
+    int hitB = 0;
+    if (newZpos > P_zetac) { double r = P_zetac - newZpos; newZpos = P_zetac + r; }
+    if (newZpos < P_depth) { double r = P_depth - newZpos; newZpos = P_depth + r; hitB++; }
+    newZpos = newZpos + bo.Z;
+    if (P.Behavior == 7) {
+        if (bo.bott) { newXpos = Xpar; newYpos = Ypar; newZpos = P_depth; }
+        else { newXpos = newXpos + bo.X; newYpos = newYpos + bo.Y; newZpos = P_depth + P.Swimdepth; }
+    }
+    if (newZpos > P_zetac) newZpos = P_zetac - eps6;
+    if (newZpos < P_depth) { newZpos = P_depth + eps6; hitB++; }
+    if (P.TrackCollisions && hitB) D.hitB[n] += hitB;
+
+    double Xpos = Xpar, Ypos = Ypar, nXpos = newXpos, nYpos = newYpos;  // :1180-1232
+    int skip = -1, reflects = 0, hitL = 0;
+    for (;;) {
+        Hit h;
+        if (!intersect_reflect2(D, Xpos, Ypos, nXpos, nYpos, skip, h)) break;
+        skip = h.seg;
+        hitL++;
+        if (P.OpenOceanBoundary && h.water) {
+            D.x[n] = h.ix; D.y[n] = h.iy; D.z[n] = newZpos;
+            D.flags[n] |= LT_F_OOB;
+            if (P.TrackCollisions) D.hitL[n] += hitL;
+            return;
+        }
+        if (++reflects > 3) {
+            if (P.TrackCollisions) D.hitL[n] += hitL;
+            particle_error(D, n, LTGPU_EV_OUT_3RD, Zpar);
+            return;
+        }
+        Xpos = h.ix; Ypos = h.iy; nXpos = h.rx; nYpos = h.ry;
+    }
+    if (P.TrackCollisions && hitL) D.hitL[n] += hitL;
+    newXpos = nXpos; newYpos = nYpos;
+    {                                                                    // mbounds :1240
+        int in = inpoly_banded(newXpos, newYpos, D.bxy, D.mb_y0, D.mb_rbh, D.mb_n, D.mb_ptr, D.mb_idx);
+        if (in == 2) in = inpoly(newXpos, newYpos, D.maxbound, D.bxy, false) ? 1 : 0;
+        if (!in) { particle_error(D, n, LTGPU_EV_OUT_MAIN, Zpar); return; }
+    }
+    if (D.maxisland > 0) {                                               // ibounds :1275
+        int in = D.ib_ok ? inpoly_banded(newXpos, newYpos, D.hxy, D.ib_y0, D.ib_rbh, D.ib_n, D.ib_ptr, D.ib_idx) : 2;
+        if (in == 2) in = in_any_island(D, newXpos, newYpos) ? 1 : 0;
+        if (in) { particle_error(D, n, LTGPU_EV_IN_ISLAND, Zpar); return; }
+    }
+    D.x[n] = newXpos; D.y[n] = newYpos; D.z[n] = newZpos;                // commit :1312-1314, :1407-1414
+    {                                                                    // setEle at the new position :1317
+        int err = 0, re0 = re, ue0 = ue, ve0 = ve;
+        if (!find_element(D.R, newXpos, newYpos, re)) err = 4;
+        if (!find_element(D.U, newXpos, newYpos, ue)) err = 5;
+        if (!find_element(D.V, newXpos, newYpos, ve)) err = 6;
+        if (re != re0) D.r_ele[n] = re;
+        if (ue != ue0) D.u_ele[n] = ue;
+        if (ve != ve0) D.v_ele[n] = ve;
+        if (err) {
+            if (P.ErrorFlag == 1) { D.x[n] = Xpar; D.y[n] = Ypar; }
+            particle_error(D, n, err == 4 ? LTGPU_EV_JUMP_RHO : err == 5 ? LTGPU_EV_JUMP_U : LTGPU_EV_JUMP_V, Zpar);
+            return;
+        }
+    }
+    if (P.settlementon) {                                                // :1373-1382, ledger 14
+        int inp = test_settlement(D, age, re, Xpar, Ypar);
+        if (inp > 0) {
+            D.flags[n] |= LT_F_SETTLED;
+            D.z[n] = P_depth; D.endpoly[n] = inp; D.lifespan[n] = age;
+        }
+    }
+}

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include "lt_step.cuh"
+#include "lt_step2.cuh"
 
 // ------------------------------------------------------------------ kernels --
 template <class T>
@@ -22,6 +23,25 @@ __global__ void __launch_bounds__(128) k_step(const __grid_constant__ LtDev D)
     size_t tslot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t n = tslot; n < (size_t)D.n; n += stride) step_particle<T>(D, (int)n, tslot);
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) k_advect(const __grid_constant__ LtDev D)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < D.n) advect_particle<T>(D, n);
+}
+template <class T>
+__global__ void __launch_bounds__(128) k_vturb(const __grid_constant__ LtDev D)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < D.n) vturb_particle<T>(D, n);
+}
+template <class T>
+__global__ void __launch_bounds__(128) k_finish(const __grid_constant__ LtDev D)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < D.n) finish_particle<T>(D, n);
 }
 
 // one ROMS record [level][node] (+ mask multiply, hydro:1371-1403) -> ring slot of the
@@ -120,6 +140,7 @@ struct ltgpu_ctx {
     std::string err;
     bool have_grid = false, have_bounds = false, have_particles = false, have_habitat = false;
     int nthreads_grid = 0;
+    bool v1 = false;                         // LTGPU_KERNEL=v1: the fused first-generation kernel (A/B checks)
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -169,6 +190,103 @@ static void fill_all(ltgpu_ctx* ctx, const uint8_t* dbase, const size_t off[7], 
     }
 }
 
+// ---- exact spatial indices over the boundary tables (used by k_finish) ----------------
+// The bucket / band of a coordinate is floor((v - origin) * scale) in IEEE double on both
+// host and device; that map is monotone, which is all the exactness argument needs.
+static void csr_from_lists(const std::vector<std::vector<int>>& lists, std::vector<int>& ptr, std::vector<int>& idx)
+{
+    ptr.assign(lists.size() + 1, 0);
+    for (size_t i = 0; i < lists.size(); ++i) ptr[i + 1] = ptr[i] + (int)lists[i].size();
+    idx.clear(); idx.reserve(ptr.back());
+    for (auto& l : lists) idx.insert(idx.end(), l.begin(), l.end());
+}
+static void band_index(const std::vector<double2>& poly, const std::vector<char>& edge_ok, double& y0, double& rbh, int& nband,
+                       std::vector<int>& ptr, std::vector<int>& idx)
+{
+    int n = (int)poly.size();
+    double ymin = 1e300, ymax = -1e300;
+    for (auto& q : poly) { ymin = std::min(ymin, q.y); ymax = std::max(ymax, q.y); }
+    double ext = std::max(ymax - ymin, 1e-9);
+    nband = std::max(1, std::min(8192, n / 2));
+    y0 = ymin - 1e-6 * ext;
+    rbh = (double)nband / (ext * (1.0 + 2e-6));
+    std::vector<std::vector<int>> lists(nband);
+    for (int i = 0; i + 1 < n; ++i) {
+        if (!edge_ok[i]) continue;
+        double lo = std::min(poly[i].y, poly[i + 1].y), hi = std::max(poly[i].y, poly[i + 1].y);
+        int b0 = std::max(0, std::min(nband - 1, (int)floor((lo - y0) * rbh)));
+        int b1 = std::max(0, std::min(nband - 1, (int)floor((hi - y0) * rbh)));
+        for (int bq = b0; bq <= b1; ++bq) lists[bq].push_back(i);
+    }
+    csr_from_lists(lists, ptr, idx);
+}
+static bool host_inpoly(double x, double y, const double2* e, int n)
+{   // plain crossing test, only used to validate that islands are not nested
+    bool in = false;
+    for (int i = 0, j = n - 1; i < n; j = i++)
+        if (((e[i].y > y) != (e[j].y > y)) && (x < (e[j].x - e[i].x) * (y - e[i].y) / (e[j].y - e[i].y) + e[i].x)) in = !in;
+    return in;
+}
+static int32_t build_indices(ltgpu_ctx* ctx, const std::vector<double4>& seg, const std::vector<double2>& b,
+                             const std::vector<double2>& h, const int32_t* hid)
+{
+    LtDev& D = ctx->D;
+    int ns = (int)seg.size();
+    // segment buckets
+    {
+        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+        std::vector<double> len(ns);
+        for (int i = 0; i < ns; ++i) {
+            xmin = std::min({xmin, seg[i].x, seg[i].z}); xmax = std::max({xmax, seg[i].x, seg[i].z});
+            ymin = std::min({ymin, seg[i].y, seg[i].w}); ymax = std::max({ymax, seg[i].y, seg[i].w});
+            len[i] = hypot(seg[i].z - seg[i].x, seg[i].w - seg[i].y);
+        }
+        double cs = 1.0;
+        if (ns) { std::vector<double> t = len; std::nth_element(t.begin(), t.begin() + ns / 2, t.end()); cs = std::max(2.0 * t[ns / 2], 1e-9); }
+        else { xmin = ymin = 0; xmax = ymax = 1; }
+        while ((xmax - xmin) / cs * ((ymax - ymin) / cs) > 4.0e6) cs *= 1.5;
+        D.sg_x0 = xmin - cs; D.sg_y0 = ymin - cs; D.sg_rcs = 1.0 / cs;
+        D.sg_nx = (int)floor((xmax - D.sg_x0) * D.sg_rcs) + 2; D.sg_ny = (int)floor((ymax - D.sg_y0) * D.sg_rcs) + 2;
+        std::vector<std::vector<int>> lists((size_t)D.sg_nx * D.sg_ny);
+        for (int i = 0; i < ns; ++i) {
+            int cx0 = (int)floor((std::min(seg[i].x, seg[i].z) - D.sg_x0) * D.sg_rcs), cx1 = (int)floor((std::max(seg[i].x, seg[i].z) - D.sg_x0) * D.sg_rcs);
+            int cy0 = (int)floor((std::min(seg[i].y, seg[i].w) - D.sg_y0) * D.sg_rcs), cy1 = (int)floor((std::max(seg[i].y, seg[i].w) - D.sg_y0) * D.sg_rcs);
+            for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) lists[(size_t)cy * D.sg_nx + cx].push_back(i);
+        }
+        std::vector<int> ptr, idx; csr_from_lists(lists, ptr, idx);
+        TRY(upload(ctx, &D.sg_ptr, ptr.data(), ptr.size()));
+        TRY(upload(ctx, &D.sg_idx, idx.data(), idx.size()));
+    }
+    // main polygon bands
+    {
+        std::vector<char> ok(b.size(), 1);
+        std::vector<int> ptr, idx;
+        if (b.size() >= 2) band_index(b, ok, D.mb_y0, D.mb_rbh, D.mb_n, ptr, idx);
+        else { D.mb_n = 0; D.mb_y0 = 0; D.mb_rbh = 0; ptr.assign(1, 0); }
+        TRY(upload(ctx, &D.mb_ptr, ptr.data(), ptr.size()));
+        TRY(upload(ctx, &D.mb_idx, idx.data(), idx.size()));
+    }
+    // island bands: one joint crossing count over all islands is "in any island" only if the
+    // islands are disjoint and not nested; otherwise the per-island routine is used (ib_ok = 0)
+    {
+        int nh = (int)h.size();
+        std::vector<char> ok(nh, 1);
+        std::vector<int> start;
+        for (int i = 0; i < nh; ++i) { if (i == 0 || hid[i] != hid[i - 1]) start.push_back(i); if (i + 1 < nh && hid[i + 1] != hid[i]) ok[i] = 0; }
+        start.push_back(nh);
+        D.ib_ok = 1;
+        for (size_t a = 0; a + 1 < start.size() && D.ib_ok; ++a)
+            for (size_t c = 0; c + 1 < start.size(); ++c)
+                if (a != c && host_inpoly(h[start[a]].x, h[start[a]].y, h.data() + start[c], start[c + 1] - start[c] - 1)) { D.ib_ok = 0; break; }
+        std::vector<int> ptr, idx;
+        if (nh >= 2) band_index(h, ok, D.ib_y0, D.ib_rbh, D.ib_n, ptr, idx);
+        else { D.ib_n = 0; D.ib_y0 = 0; D.ib_rbh = 0; ptr.assign(1, 0); }
+        TRY(upload(ctx, &D.ib_ptr, ptr.data(), ptr.size()));
+        TRY(upload(ctx, &D.ib_idx, idx.data(), idx.size()));
+    }
+    return LTGPU_OK;
+}
+
 extern "C" {
 
 int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
@@ -199,6 +317,8 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming);
     cudaEventCreate(&ctx->t0); cudaEventCreate(&ctx->t1);
     ctx->D.sb = 0; ctx->D.sc = 1; ctx->D.sf = 2; ctx->spare = 3;
+    const char* kv = getenv("LTGPU_KERNEL");
+    ctx->v1 = kv && strcmp(kv, "v1") == 0;
     *out = ctx;
     return LTGPU_OK;
 }
@@ -331,6 +451,7 @@ int32_t ltgpu_set_bounds(ltgpu_ctx* ctx, int32_t nbounds, const double* bnd_x, c
     TRY(upload(ctx, &D.hxy, h.data(), h.size()));
     TRY(upload(ctx, &D.hid, hid, (size_t)maxisland));
     D.nbounds = nbounds; D.maxbound = maxbound; D.maxisland = maxisland;
+    TRY(build_indices(ctx, seg, b, h, hid));
     ctx->have_bounds = true;
     return LTGPU_OK;
 }
@@ -403,10 +524,14 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
     CK(cudaMemsetAsync(ctx->d_nev, 0, 4, ctx->compute));
     k_fill_i32<<<1, 32, 0, ctx->compute>>>(ctx->d_bad, INT_MAX, 1);
     TRY(dalloc(ctx, &ctx->d_stats, 8)); TRY(dalloc(ctx, &ctx->d_status, N));
-    // VTurb scratch: 7 arrays of (4*ws + 8) doubles per resident thread
+    double** sc[] = {&D.s_depth, &D.s_angle, &D.s_zeb, &D.s_zec, &D.s_zef, &D.s_pzb, &D.s_pzc, &D.s_pzf, &D.s_zpar,
+                     &D.s_nx, &D.s_ny, &D.s_advz, &D.s_pu, &D.s_pv, &D.s_turbv};
+    for (auto p : sc) TRY(dalloc(ctx, p, N));
+    TRY(dalloc(ctx, &D.s_act, N));
+    // v1 VTurb scratch: 7 arrays of (4*ws + 8) doubles per resident thread
     int threads = (int)std::min<size_t>((size_t)ctx->nthreads_grid, ((N + 127) / 128) * 128);
     ctx->nthreads_grid = threads;
-    if (ctx->prm.VTurbOn) {
+    if (ctx->prm.VTurbOn && ctx->v1) {
         D.vt_p2 = 4 * ctx->prm.ws; D.vt_stride = threads;
         TRY(dalloc(ctx, &D.vt, (size_t)7 * (D.vt_p2 + 8) * (size_t)threads));
     }
@@ -487,11 +612,37 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
     D.ix[1] = D.ex[1] + (double)((it - 1) * idt);
     D.ix[2] = D.ex[1] + (double)(it * idt);
     D.gstep = (unsigned)((p - 1) * (dt / idt) + it);
-    int blocks = ctx->nthreads_grid / 128;
-    if (ctx->esz == 4) k_step<float><<<blocks, 128, 0, ctx->compute>>>(D);
-    else k_step<double><<<blocks, 128, 0, ctx->compute>>>(D);
+    {   // Lagrange weights of the 3-point time polynomial at ix(1..3); p == 1 uses (b,b,c) (LTRANS.f90:1534-1544)
+        const double e0 = D.ex[0], e1 = D.ex[1], e2 = D.ex[2];
+        for (int v = 0; v < 3; ++v) {
+            double x = D.ix[v];
+            double L0 = (x - e1) * (x - e2) / ((e0 - e1) * (e0 - e2)), L1 = (x - e0) * (x - e2) / ((e1 - e0) * (e1 - e2)),
+                   L2 = (x - e0) * (x - e1) / ((e2 - e0) * (e2 - e1));
+            if (v == 1) { D.LWz[0] = L0; D.LWz[1] = L1; D.LWz[2] = L2; }
+            if (p == 1) { D.LW[v][0] = L0 + L1; D.LW[v][1] = L2; D.LW[v][2] = 0.0; }
+            else { D.LW[v][0] = L0; D.LW[v][1] = L1; D.LW[v][2] = L2; }
+        }
+        for (int t = 0; t < 3; ++t) D.LW4[t] = (D.LW[0][t] + 4.0 * D.LW[1][t] + D.LW[2][t]) / 6.0;
+    }
+    if (ctx->v1) {
+        int blocks = ctx->nthreads_grid / 128;
+        if (ctx->esz == 4) k_step<float><<<blocks, 128, 0, ctx->compute>>>(D);
+        else k_step<double><<<blocks, 128, 0, ctx->compute>>>(D);
+        ctx->launches++;
+    } else {
+        int blocks = (D.n + 127) / 128;
+        if (ctx->esz == 4) {
+            k_advect<float><<<blocks, 128, 0, ctx->compute>>>(D);
+            if (ctx->prm.VTurbOn) k_vturb<float><<<blocks, 128, 0, ctx->compute>>>(D);
+            k_finish<float><<<blocks, 128, 0, ctx->compute>>>(D);
+        } else {
+            k_advect<double><<<blocks, 128, 0, ctx->compute>>>(D);
+            if (ctx->prm.VTurbOn) k_vturb<double><<<blocks, 128, 0, ctx->compute>>>(D);
+            k_finish<double><<<blocks, 128, 0, ctx->compute>>>(D);
+        }
+        ctx->launches += ctx->prm.VTurbOn ? 3 : 2;
+    }
     CK(cudaGetLastError());
-    ctx->launches++;
     ctx->last_ix3 = D.ix[2];
     return LTGPU_OK;
 }

@@ -245,8 +245,10 @@ static int ypc1(int N, const double* X, const double* Y, double* YP)
 
 /* tension_module.f90:314-782  SIGS as modified in LTRANS (TOL = 0, zeroed
  * SIGMA on entry, NIT cap 10000 -> SigErr).  Ledger 18: logical CONT is not
- * assigned on the SIG <= 0.5 secant branch; restated as initialised .TRUE. on
- * entry and carried (what -finit-logical=true gives).                        */
+ * assigned on the SIG <= 0.5 secant branch (undefined in the reference; TSPACK's
+ * original always evaluates F there); restated as .TRUE. at the start of every
+ * interval and carried between that interval's iterations, which keeps intervals
+ * independent of one another.                                                 */
 static void sigs(int N, const double* X, const double* Y, const double* YP, double* SIGMA,
                  int* IER, int* SigErr)
 {
@@ -260,8 +262,7 @@ static void sigs(int N, const double* X, const double* Y, const double* YP, doub
     for (;;) { RTOL = RTOL / 2.0; one_plus = RTOL + 1.0; if (one_plus <= 1.0) break; }
     RTOL = RTOL * 200.0;                                    /* :433-439 */
     int ICNT = 0; double DSM = 0.0;
-    int CONT = 1, FLAG = 0;
-    double A = 0.0, E = 0.0;
+    int FLAG = 0;
 #define STORE_SIG() do { SIG = fmin(SIG, SBIG); if (SIG > SIGIN) { SIGMA[I - 1] = SIG; ICNT++; \
         DSIG = SIG - SIGIN; if (SIGIN > 0.0) DSIG = DSIG / SIGIN; DSM = fmax(DSM, DSIG); } } while (0)
     for (int I = 1; I <= NM1; ++I) {
@@ -270,6 +271,8 @@ static void sigs(int N, const double* X, const double* Y, const double* YP, doub
         if (DX <= 0.0) { *IER = -IP1; (void)DSM; return; }
         double SIGIN = SIGMA[I - 1];
         if (SIGIN >= SBIG) continue;
+        int CONT = 1;                                       /* ledger 18: .TRUE. per interval */
+        double A = 0.0, E = 0.0;
         double S1 = YP[I - 1], S2 = YP[IP1 - 1];
         double S = (Y[IP1 - 1] - Y[I - 1]) / DX;
         double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
