@@ -334,6 +334,11 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
         double TP1 = T + 1.0;
         SIG = sqrt(10.0 * T - 20.0);
         int NIT = 0;
+        // Newton's map SIG -> SIG' is a pure function of SIG.  When F's rounding noise sits
+        // just above RTOL the iteration falls into a short cycle and the reference spins until
+        // NIT > 10000 and raises SigErr (tension:556-559).  A repeated iterate proves the
+        // cycle, so Brent's checkpointing reaches the same verdict without 10^4 iterations.
+        double chk = SIG; int chk_at = 1;
         for (;;) {
             double T1, FP;
             if (SIG <= .5) {
@@ -355,6 +360,8 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
             double DSIG = -qdiv(F, FP);
             if (fabs(DSIG) <= RTOL * SIG || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
             SIG = SIG + DSIG;
+            if (SIG == chk) { err = 1; return 0.0; }
+            if (NIT == chk_at) { chk = SIG; chk_at <<= 1; }
         }
         return fmin(SIG, SBIG);
     }

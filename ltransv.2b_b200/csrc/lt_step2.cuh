@@ -85,7 +85,10 @@ LT_DEV Wt make_weights2(const double* __restrict__ q, double xp, double yp, bool
     return w;
 }
 
-LT_DEV double lag(const double* w, double b, double c, double f) { return w[0] * b + w[1] * c + w[2] * f; }
+// Lagrange weights applied to DIFFERENCES from the centre value: like polintd, this
+// returns the data exactly when the three values are equal (a particle resting on the
+// bed must not drift by an ulp), and the weights need not sum to one in floating point.
+LT_DEV double lag(const double* w, double b, double c, double f) { return c + (w[0] * (b - c) + w[2] * (f - c)); }
 
 // 4-knot spline value (TSPSI + HVAL of WCTS_ITPI, hydro:2619-2644) with the knot
 // reciprocals shared between the fields interpolated on the same knots.
@@ -488,6 +491,9 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
         if ((i & 1) == 0) rnd = philox(g, 1u + (unsigned)(i >> 1));
         const double DEV = (i & 1) ? box_muller(D, rnd.z, rnd.w) : box_muller(D, rnd.x, rnd.y);
         ParZc = ParZc + KprimeZc + DEV * sqrt(2.0 * KH3rdc * deltat);  // (...)**0.5, ledger 12
+#ifdef LT_DEBUG_TRACE
+        if (D.first_id + n == D.dbg_id) { D.dbg[4 * i] = ParZc; D.dbg[4 * i + 1] = Kprimec; D.dbg[4 * i + 2] = KH3rdc; D.dbg[4 * i + 3] = DEV; }
+#endif
     }
     D.s_turbv[n] = P_zc - ParZc;                                        // :342
 }

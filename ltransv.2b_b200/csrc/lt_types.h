@@ -64,6 +64,9 @@ struct LtDev {
     double sg_x0, sg_y0, sg_rcs; int sg_nx, sg_ny; const int *sg_ptr, *sg_idx;     // segment buckets
     double mb_y0, mb_rbh; int mb_n; const int *mb_ptr, *mb_idx;                     // main polygon y-bands
     double ib_y0, ib_rbh; int ib_n; const int *ib_ptr, *ib_idx; int ib_ok;          // island y-bands
+#ifdef LT_DEBUG_TRACE
+    double* dbg; long long dbg_id;   // debug builds only: per-substep VTurb trace of one particle
+#endif
     // this step
     int p, it; unsigned gstep;
     double ex[3], ix[3];

@@ -619,7 +619,9 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
             double L0 = (x - e1) * (x - e2) / ((e0 - e1) * (e0 - e2)), L1 = (x - e0) * (x - e2) / ((e1 - e0) * (e1 - e2)),
                    L2 = (x - e0) * (x - e1) / ((e2 - e0) * (e2 - e1));
             if (v == 1) { D.LWz[0] = L0; D.LWz[1] = L1; D.LWz[2] = L2; }
-            if (p == 1) { D.LW[v][0] = L0 + L1; D.LW[v][1] = L2; D.LW[v][2] = 0.0; }
+            // lag() uses y_c + w0 (y_b - y_c) + w2 (y_f - y_c); the p == 1 triplet (b,b,c) is
+            // b + L2 (c - b) = y_c + (1 - L2)(y_b - y_c) + 0 (y_f - y_c)
+            if (p == 1) { D.LW[v][0] = 1.0 - L2; D.LW[v][1] = L2; D.LW[v][2] = 0.0; }
             else { D.LW[v][0] = L0; D.LW[v][1] = L1; D.LW[v][2] = L2; }
         }
         for (int t = 0; t < 3; ++t) D.LW4[t] = (D.LW[0][t] + 4.0 * D.LW[1][t] + D.LW[2][t]) / 6.0;
@@ -771,6 +773,16 @@ int32_t ltgpu_timer_stop(ltgpu_ctx* ctx, float* ms)
     CK(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
     return LTGPU_OK;
 }
+#ifdef LT_DEBUG_TRACE
+int32_t ltgpu_debug_trace(ltgpu_ctx* ctx, int64_t id, double* out, int32_t n)
+{   // debug builds only (never compiled into the shipped library)
+    if (!ctx->D.dbg) { void* q; cudaMalloc(&q, 4096 * 8); cudaMemset(q, 0, 4096 * 8); ctx->D.dbg = (double*)q; }
+    cudaStreamSynchronize(ctx->compute);
+    if (out) cudaMemcpy(out, ctx->D.dbg, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    ctx->D.dbg_id = id;
+    return 0;
+}
+#endif
 int64_t ltgpu_launch_count(const ltgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* ltgpu_stream(ltgpu_ctx* ctx) { return ctx ? (void*)ctx->compute : nullptr; }
 

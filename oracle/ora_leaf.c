@@ -10,6 +10,7 @@
  * Build with -O2 -ffp-contract=off (no FMA contraction, no fast-math).
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "ltrans_oracle.h"
@@ -301,7 +302,7 @@ static void sigs(int N, const double* X, const double* Y, const double* YP, doub
                 }
                 F = SIG * T1 - TP1;
                 NIT = NIT + 1;
-                if (NIT > 10000) { *SigErr = *SigErr + 1; return; }   /* :556-559 */
+                if (NIT > 10000) { if (getenv("ORA_SIGDBG")) fprintf(stderr, "SIGDBG newton I=%d N=%d SIG=%.17g F=%.17g FP=%.17g T=%.17g D1=%.17g D2=%.17g\n", I, N, SIG, F, FP, T, D1, D2); *SigErr = *SigErr + 1; return; }   /* :556-559 */
                 FLAG = 0;
                 if (FP <= 0.0) { FLAG = 1; break; }
                 DSIG = -F / FP;
@@ -361,7 +362,7 @@ static void sigs(int N, const double* X, const double* Y, const double* YP, doub
             }
             if (CONT) F = (SGN * (E * S2 - C2) + sqrt(A * (C2 + C1))) / E;
             NIT = NIT + 1;
-            if (NIT > 100000) { *SigErr = *SigErr + 1; return; }  /* safety net, not in reference */
+            if (NIT > 100000) { if (getenv("ORA_SIGDBG")) fprintf(stderr, "SIGDBG secant I=%d N=%d SIG=%.17g F=%.17g DMAX=%.17g STOL=%.17g\n", I, N, SIG, F, DMAX, STOL); *SigErr = *SigErr + 1; return; }  /* safety net, not in reference */
             STOL = RTOL * SIG;
             if (fabs(DMAX) <= STOL || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
             DMAX = DMAX + DSIG;

@@ -741,6 +741,8 @@ static double VTurb(ora_ctx* c, const elestate* es, prng* g, double P_zc, double
         double DEV = norm_(g, 1u + (uint32_t)(q >> 1), 2 * (q & 1));
         double r = 1.;
         ParZc = ParZc + KprimeZc + DEV * pow(2.0 / r * KH3rdc * deltat, 0.5);
+        if (getenv("ORA_TRACE_ID") && atoll(getenv("ORA_TRACE_ID")) == (long long)(((uint64_t)g->id_hi << 32) | g->id_lo))
+            fprintf(stderr, "ORATRACE %d %.17g %.17g %.17g %.17g\n", i - 1, ParZc, Kprimec, KH3rdc, DEV);
     }
     double TurbV = P_zc - ParZc;                             /* :342 (ledger 11) */
     free(KHb); free(KHc); free(KHf); free(slb); free(slc); free(slf); free(icb); free(icc); free(icf);
