@@ -67,29 +67,6 @@ LT_DEV void load_bcf<double>(const double* base, size_t idx, int sb, int sc, int
     b = sel4(lo.x, lo.y, hi.x, hi.y, sb); c = sel4(lo.x, lo.y, hi.x, hi.y, sc); f = sel4(lo.x, lo.y, hi.x, hi.y, sf);
 }
 
-// ------------------------------------------------------------- polintd ------
-// interpolation_module.f90:70-107 (n = 3), same operation order.
-LT_DEV double polintd(const double* xa, double y1, double y2, double y3, double x)
-{
-    int ns = 1; double dif = fabs(x - xa[0]);
-    double d2 = fabs(x - xa[1]); if (d2 < dif) { ns = 2; dif = d2; }
-    double d3 = fabs(x - xa[2]); if (d3 < dif) { ns = 3; dif = d3; }
-    double c = (xa[1] - x) * ((y3 - y2) / (xa[1] - xa[2]));
-    c = c - (xa[1] - x) * ((y2 - y1) / (xa[0] - xa[1]));
-    c = c / (xa[0] - xa[2]);
-    double a, b;
-    if (ns == 3) { a = (y3 - y2) / (xa[1] - xa[2]); b = xa[2] - x; }
-    else         { a = (y2 - y1) / (xa[0] - xa[1]); b = xa[0] - x; }
-    double yn = ns == 1 ? y1 : ns == 2 ? y2 : y3;
-    double xn = ns == 1 ? xa[0] : ns == 2 ? xa[1] : xa[2];
-    return yn + (xn - x) * a + b * c;
-}
-// time polynomial with the p == 1 triplet (b,b,c) of LTRANS.f90:1534-1544
-LT_DEV double time_poly(const LtDev& D, double vb, double vc, double vf, double x)
-{
-    return D.p == 1 ? polintd(D.ex, vb, vb, vc, x) : polintd(D.ex, vb, vc, vf, x);
-}
-
 // ------------------------------------------------------------- gridcell -----
 // gridcell_module.f90:26-257, single element.  q = x0..x3,y0..y3.
 LT_DEVN bool gridcell(const double* __restrict__ q, double X, double Y)
@@ -146,43 +123,46 @@ LT_DEV bool find_element(const LtGridTab& G, double X, double Y, int& ele)
 }
 
 // ------------------------------------------------- interpolation weights ----
-struct Wt { int mode; double t, u; };   // 1,2: triangles (hydro:1706-1714); 3: IDW; 4..7: on node 1..4
+// mode 1,2: barycentric (t,u) in triangle (1,2,3) / (3,4,1) (hydro:1706-1714); mode 3: inverse
+// distance, the four weights are t,u,w2,w3 (hydro:1726-1735); mode 4..7: on node 1..4.
+struct Wt { int mode; double t, u, w2, w3; };
 
 // setInterp (hydro:1680-1740) when `setinterp_quirk` (an on-node point outside both
-// triangles keeps tOK = 2), interp (hydro:2533-2565) otherwise.
+// triangles keeps tOK = 2), interp (hydro:2533-2565) otherwise.  The weights are a function
+// of (element, point) only: the reference recomputes them for every interpolated value
+// (36 times per RK stage); here once per (grid, stage).
 LT_DEV Wt make_weights(const double* __restrict__ q, double xp, double yp, bool setinterp_quirk)
 {
     double x1 = q[0], x2 = q[1], x3 = q[2], x4 = q[3], y1 = q[4], y2 = q[5], y3 = q[6], y4 = q[7];
-    Wt w;
-    w.t = ((xp - x1) * (y3 - y1) + (y1 - yp) * (x3 - x1)) / ((x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1));
-    w.u = ((xp - x1) * (y2 - y1) + (y1 - yp) * (x2 - x1)) / ((x3 - x1) * (y2 - y1) - (y3 - y1) * (x2 - x1));
+    Wt w; w.w2 = 0.0; w.w3 = 0.0;
+    w.t = qdiv((xp - x1) * (y3 - y1) + (y1 - yp) * (x3 - x1), (x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1));
+    w.u = qdiv((xp - x1) * (y2 - y1) + (y1 - yp) * (x2 - x1), (x3 - x1) * (y2 - y1) - (y3 - y1) * (x2 - x1));
     w.mode = 1;
     if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
-        w.t = ((xp - x3) * (y1 - y3) + (y3 - yp) * (x1 - x3)) / ((x4 - x3) * (y1 - y3) - (y4 - y3) * (x1 - x3));
-        w.u = ((xp - x3) * (y4 - y3) + (y3 - yp) * (x4 - x3)) / ((x1 - x3) * (y4 - y3) - (y1 - y3) * (x4 - x3));
+        w.t = qdiv((xp - x3) * (y1 - y3) + (y3 - yp) * (x1 - x3), (x4 - x3) * (y1 - y3) - (y4 - y3) * (x1 - x3));
+        w.u = qdiv((xp - x3) * (y4 - y3) + (y3 - yp) * (x4 - x3), (x1 - x3) * (y4 - y3) - (y1 - y3) * (x4 - x3));
         w.mode = 2;
         if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
             bool n1 = xp == x1 && yp == y1, n2 = xp == x2 && yp == y2, n3 = xp == x3 && yp == y3, n4 = xp == x4 && yp == y4;
-            if (n1 || n2 || n3 || n4) {
-                if (!setinterp_quirk) w.mode = n4 ? 7 : n3 ? 6 : n2 ? 5 : 4;
-            } else w.mode = 3;
+            if (n1 || n2 || n3 || n4) { if (!setinterp_quirk) w.mode = n4 ? 7 : n3 ? 6 : n2 ? 5 : 4; }
+            else {
+                double D1 = rsqrt((x1 - xp) * (x1 - xp) + (y1 - yp) * (y1 - yp));
+                double D2 = rsqrt((x2 - xp) * (x2 - xp) + (y2 - yp) * (y2 - yp));
+                double D3 = rsqrt((x3 - xp) * (x3 - xp) + (y3 - yp) * (y3 - yp));
+                double D4 = rsqrt((x4 - xp) * (x4 - xp) + (y4 - yp) * (y4 - yp));
+                double rT = qrcp(D1 + D2 + D3 + D4);
+                w.t = D1 * rT; w.u = D2 * rT; w.w2 = D3 * rT; w.w3 = D4 * rT;
+                w.mode = 3;
+            }
         }
     }
     return w;
 }
-LT_DEV double combine(const Wt& w, const double* __restrict__ q, double xp, double yp,
-                      double v1, double v2, double v3, double v4)
+LT_DEV double combine(const Wt& w, double v1, double v2, double v3, double v4)
 {
     if (w.mode == 1) return v1 + (v2 - v1) * w.t + (v3 - v1) * w.u;
     if (w.mode == 2) return v3 + (v4 - v3) * w.t + (v1 - v3) * w.u;
-    if (w.mode == 3) {   // inverse distance (rare: extrapolating RK sub-stage points)
-        double D1 = 1. / sqrt((q[0] - xp) * (q[0] - xp) + (q[4] - yp) * (q[4] - yp));
-        double D2 = 1. / sqrt((q[1] - xp) * (q[1] - xp) + (q[5] - yp) * (q[5] - yp));
-        double D3 = 1. / sqrt((q[2] - xp) * (q[2] - xp) + (q[6] - yp) * (q[6] - yp));
-        double D4 = 1. / sqrt((q[3] - xp) * (q[3] - xp) + (q[7] - yp) * (q[7] - yp));
-        double TD = D1 + D2 + D3 + D4;
-        return (D1 / TD) * v1 + (D2 / TD) * v2 + (D3 / TD) * v3 + (D4 / TD) * v4;
-    }
+    if (w.mode == 3) return w.t * v1 + w.u * v2 + w.w2 * v3 + w.w3 * v4;
     return w.mode == 4 ? v1 : w.mode == 5 ? v2 : w.mode == 6 ? v3 : v4;
 }
 
@@ -240,9 +220,9 @@ LT_DEV void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Sten
         int one = grid == G_U ? 1 : 3;                       // hydro:2408
         freeslip(b, m, one, md); freeslip(c, m, one, md); freeslip(f, m, one, md);
     }
-    rb = combine(s.w, s.q, s.xp, s.yp, b[0], b[1], b[2], b[3]);
-    rc = combine(s.w, s.q, s.xp, s.yp, c[0], c[1], c[2], c[3]);
-    rf = combine(s.w, s.q, s.xp, s.yp, f[0], f[1], f[2], f[3]);
+    rb = combine(s.w, b[0], b[1], b[2], b[3]);
+    rc = combine(s.w, c[0], c[1], c[2], c[3]);
+    rf = combine(s.w, f[0], f[1], f[2], f[3]);
 }
 
 LT_DEV double gather_static(const LtDev& D, const double* arr, const Stencil& s)
@@ -252,37 +232,7 @@ LT_DEV double gather_static(const LtDev& D, const double* arr, const Stencil& s)
         int m[4] = { D.R.mask[s.nd.x], D.R.mask[s.nd.y], D.R.mask[s.nd.z], D.R.mask[s.nd.w] };
         freeslip(v, m, 3, m);
     }
-    return combine(s.w, s.q, s.xp, s.yp, v[0], v[1], v[2], v[3]);
-}
-
-// --------------------------------------------------------------- s-levels ---
-// getSlevel / getWlevel (hydro:2691-2777); depth < 0, hc widened from REAL(4).
-LT_DEV double zlevel(const LtDev& D, double zeta, double depth, double sc, double cs)
-{
-    double hc = (double)D.P.hc, h = -1.0 * depth, S;
-    if (D.P.Vtransform == 1) { S = hc * sc + (h - hc) * cs; return S + zeta * (1.0 + qdiv(S, h)); }
-    if (D.P.Vtransform == 2) { S = qdiv(hc * sc + h * cs, hc + h); return zeta + (zeta + h) * S; }
-    return zeta * (1.0 + sc) + hc * sc + (h - hc) * cs;
-}
-struct Column { double zb, zc, zf, depth; };     // zeta at the 3 times + (negative) depth
-LT_DEV double zr(const LtDev& D, const Column& c, double zeta, int k) { return zlevel(D, zeta, c.depth, D.SC[k], D.CS[k]); }
-LT_DEV double zw(const LtDev& D, const Column& c, double zeta, int k) { return zlevel(D, zeta, c.depth, D.SCW[k], D.CSW[k]); }
-
-// first i in [3, n-2] (1-based) with Z below level i at any of the 3 times, else n-1;
-// returns i-2 (LTRANS.f90:1451-1467).  Levels increase with i, so the linear scan of
-// the reference is a lower_bound: bisect.
-template <bool W>
-LT_DEV int level_window(const LtDev& D, const Column& c, double Z, int n)
-{
-    int lo = 3, hi = n - 1;          // answer i in [3, n-1]
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;    // test level mid (1-based) -> index mid-1
-        double sc = W ? D.SCW[mid - 1] : D.SC[mid - 1], cs = W ? D.CSW[mid - 1] : D.CS[mid - 1];
-        bool below = Z < zlevel(D, c.zb, c.depth, sc, cs) || Z < zlevel(D, c.zc, c.depth, sc, cs) ||
-                     Z < zlevel(D, c.zf, c.depth, sc, cs);
-        if (below) hi = mid; else lo = mid + 1;
-    }
-    return lo - 2;
+    return combine(s.w, v[0], v[1], v[2], v[3]);
 }
 
 // ---------------------------------------------------------------- TSPACK ----
@@ -481,54 +431,6 @@ LT_DEV double ypc1_mid_r(double DXIM1, double DXI, double SIM1, double SI, doubl
 
 // TSPSI(N=4) + HVAL, or the linint fallback: the water-column profile value of
 // WCTS_ITPI (hydro:2619-2644) at T.
-LT_DEVN double spline4_eval(const double* __restrict__ X, const double* __restrict__ Y, double T)
-{
-    double dx1 = X[1] - X[0], dx2 = X[2] - X[1], dx3 = X[3] - X[2];
-    double s1 = (Y[1] - Y[0]) / dx1, s2 = (Y[2] - Y[1]) / dx2, s3 = (Y[3] - Y[2]) / dx3;
-    double YP[4];
-    YP[0] = ypc1_end(s1, s1 + dx1 * (s1 - s2) / (dx1 + dx2));
-    YP[1] = ypc1_mid(dx1, dx2, s1, s2);
-    YP[2] = ypc1_mid(dx2, dx3, s2, s3);
-    YP[3] = ypc1_end(s3, s3 + dx3 * (s3 - s2) / (dx2 + dx3));
-    int I;                                      // HVAL interval (0-based), INTRVL bisection for N = 4
-    if (T < X[0]) I = 0; else if (T > X[3]) I = 2;
-    else { I = T < X[2] ? (T < X[1] ? 0 : 1) : 2; }
-    int err = 0;
-    double sig = sigs_interval(X[I + 1] - X[I], Y[I], Y[I + 1], YP[I], YP[I + 1], err);
-    if (err == 0) return hval_interval(T, X[I], X[I + 1], Y[I], Y[I + 1], YP[I], YP[I + 1], sig);
-    // linint (interpolation_module.f90:25-59), n = 4
-    int jlo = 1, jhi = 4;
-    for (;;) { int k = (jhi + jlo) / 2; if (X[k - 1] > T) jhi = k; else jlo = k; if (jhi - jlo == 1) break; }
-    double m = (Y[jlo - 1] - Y[jhi - 1]) / (X[jlo - 1] - X[jhi - 1]);
-    double b = Y[jlo - 1] - m * X[jlo - 1];
-    return m * T + b;
-}
-
-// WCTS_ITPI (hydro:2577-2689): 4-level profile at 3 times -> spline at P_z{b,c,f}
-// -> time polynomial.  v = 1,2,3: value at ix(v); v = 4: (b + 4c + f)/6.
-template <class T, bool W>
-LT_DEV double wcts(const LtDev& D, const T* fld, int L, const Stencil& s, int grid, int4 und, const Column& col,
-                   int deplvl, double P_zb, double P_zc, double P_zf, int v)
-{
-    double zb[4], zc[4], zf[4], vb[4], vc[4], vf[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int k = deplvl - 1 + i;
-        double sc = W ? D.SCW[k] : D.SC[k], cs = W ? D.CSW[k] : D.CS[k];
-        zb[i] = zlevel(D, col.zb, col.depth, sc, cs);
-        zc[i] = zlevel(D, col.zc, col.depth, sc, cs);
-        zf[i] = zlevel(D, col.zf, col.depth, sc, cs);
-        gather_bcf<T>(D, fld, L, k, s, grid, und, vb[i], vc[i], vf[i]);
-    }
-    double P_vb = spline4_eval(zb, vb, P_zb);
-    double P_vc = spline4_eval(zc, vc, P_zc);
-    double P_vf = D.p == 1 ? 0.0 : spline4_eval(zf, vf, P_zf);
-    if (v <= 3) return time_poly(D, P_vb, P_vc, P_vf, D.ix[v - 1]);
-    double rb = time_poly(D, P_vb, P_vc, P_vf, D.ix[0]);
-    double rc = time_poly(D, P_vb, P_vc, P_vf, D.ix[1]);
-    double rf = time_poly(D, P_vb, P_vc, P_vf, D.ix[2]);
-    return (rb + rc * 4 + rf) / 6.0;
-}
 
 // ---------------------------------------------------------------- Philox ----
 // Philox4x32-10, key = (seed, 0), counter = (id_lo, id_hi, step, block): see
@@ -556,6 +458,7 @@ LT_DEV double box_muller(const LtDev& D, unsigned w1, unsigned w2)
 }
 
 // -------------------------------------------------------------- boundary ----
+struct Hit { double ix, iy, rx, ry; int seg; bool water; };
 // inpoly (point_in_polygon_module.f90:25-167) on a double2 vertex list.
 LT_DEVN bool inpoly(double x, double y, int n, const double2* __restrict__ e, bool onout)
 {
@@ -628,75 +531,6 @@ LT_DEV bool in_any_island(const LtDev& D, double x, double y)
 // intersect_reflect (boundary_module.f90:1620-1902): nearest intersection of the
 // move (Xpos,Ypos)->(nXpos,nYpos) with any boundary segment, mirror image of the end
 // point, strict `<` nearest with first index winning.
-struct Hit { double ix, iy, rx, ry; int seg; bool water; };
-LT_DEVN bool intersect_reflect(const LtDev& D, double Xpos, double Ypos, double nXpos, double nYpos,
-                               int skipbound, Hit& h)
-{
-    double xhigh = fmax(Xpos, nXpos), xlow = fmin(Xpos, nXpos), yhigh = fmax(Ypos, nYpos), ylow = fmin(Ypos, nYpos);
-    double dtest = 999999.;
-    bool found = false;
-    double rPx = 0.0, rPy = 0.0;         // ledger 19: kept from the previous segment when dist1 == dist2
-    for (int i = 0; i < D.nbounds; ++i) {
-        if (i == skipbound) continue;
-        const double2* sp = reinterpret_cast<const double2*>(D.seg + i);
-        double2 s1_ = __ldg(sp), s2_ = __ldg(sp + 1);
-        double bcx1 = s1_.x, bcy1 = s1_.y, bcx2 = s2_.x, bcy2 = s2_.y;
-        if ((bcx1 > xhigh && bcx2 > xhigh) || (bcx1 < xlow && bcx2 < xlow) ||
-            (bcy1 > yhigh && bcy2 > yhigh) || (bcy1 < ylow && bcy2 < ylow)) continue;
-        double bxhigh = fmax(bcx1, bcx2), bxlow = fmin(bcx1, bcx2), byhigh = fmax(bcy1, bcy2), bylow = fmin(bcy1, bcy2);
-        double ix, iy, rx1, ry1, rx2, ry2;
-        int kind;           // 0 none, 1 mirror in x, 2 mirror in y, 3 general mirror
-        double Mbc = 0.0, dPBC = 0.0;
-        if (bcx1 == bcx2 || nXpos == Xpos) {
-            if (bcx1 == bcx2 && nXpos == Xpos) continue;
-            if (bcx1 == bcx2 && nYpos == Ypos) {
-                ix = bcx1; iy = nYpos; kind = 1;
-                dPBC = sqrt((ix - nXpos) * (ix - nXpos) + (iy - nYpos) * (iy - nYpos));
-            } else if (nXpos == Xpos && bcy1 == bcy2) {
-                ix = nXpos; iy = bcy1; kind = 2;
-                dPBC = sqrt((ix - nXpos) * (ix - nXpos) + (iy - nYpos) * (iy - nYpos));
-            } else if (bcx1 == bcx2 && nYpos != Ypos) {
-                double Mp = (nYpos - Ypos) / (nXpos - Xpos), Bp = Ypos - Mp * Xpos;
-                ix = bcx1; iy = Mp * ix + Bp; kind = 1;
-                dPBC = nXpos - ix;
-            } else if (nXpos == Xpos && bcy1 != bcy2) {
-                Mbc = (bcy2 - bcy1) / (bcx2 - bcx1);
-                double Bbc = bcy2 - Mbc * bcx2;
-                ix = nXpos; iy = Mbc * ix + Bbc; kind = 3;
-            } else continue;
-        } else {
-            Mbc = (bcy2 - bcy1) / (bcx2 - bcx1);
-            double Bbc = bcy2 - Mbc * bcx2;
-            double Mp = (nYpos - Ypos) / (nXpos - Xpos), Bp = Ypos - Mp * Xpos;
-            ix = (Bbc - Bp) / (Mp - Mbc);
-            iy = Mp * ix + Bp;
-            if (Mbc == 0.0) { iy = byhigh; kind = 2; dPBC = nYpos - bcy1; } else kind = 3;
-        }
-        bool inbox = ix <= xhigh && ix >= xlow && iy <= yhigh && iy >= ylow &&
-                     ix <= bxhigh && ix >= bxlow && iy <= byhigh && iy >= bylow;
-        if (!inbox) continue;
-        if (kind == 1) { rx1 = nXpos + (2.0 * dPBC); ry1 = nYpos; rx2 = nXpos - (2.0 * dPBC); ry2 = nYpos; }
-        else if (kind == 2) { rx1 = nXpos; ry1 = nYpos + (2.0 * dPBC); rx2 = nXpos; ry2 = nYpos - (2.0 * dPBC); }
-        else {
-            double distBC = sqrt((bcx1 - bcx2) * (bcx1 - bcx2) + (bcy1 - bcy2) * (bcy1 - bcy2));
-            double crossk = ((nXpos - bcx1) * (bcy2 - bcy1)) - ((bcx2 - bcx1) * (nYpos - bcy1));
-            dPBC = sqrt(crossk * crossk) / distBC;
-            double mP = -1.0 / Mbc, bP = nYpos - mP * nXpos;
-            double rr = sqrt(((2.0 * dPBC) * (2.0 * dPBC)) / (1.0 + mP * mP));
-            rx1 = rr + nXpos; ry1 = mP * rx1 + bP;
-            rx2 = rr * -1.0 + nXpos; ry2 = mP * rx2 + bP;
-        }
-        double dist1 = sqrt((ix - rx1) * (ix - rx1) + (iy - ry1) * (iy - ry1));
-        double dist2 = sqrt((ix - rx2) * (ix - rx2) + (iy - ry2) * (iy - ry2));
-        if (dist1 < dist2) { rPx = rx1; rPy = ry1; } else if (dist1 > dist2) { rPx = rx2; rPy = ry2; }
-        double d = sqrt((Xpos - ix) * (Xpos - ix) + (Ypos - iy) * (Ypos - iy));
-        if (d < dtest) {
-            h.ix = ix; h.iy = iy; h.rx = rPx; h.ry = rPy; h.seg = i; h.water = !__ldg(D.land + i);
-            dtest = d; found = true;
-        }
-    }
-    return found;
-}
 
 // ------------------------------------------------------------ settlement ----
 // testSettlement / psettle / hsettle (settlement_module.f90:485-622).  Polygon edge

@@ -65,26 +65,6 @@ LT_DEV int level_window2(const LtDev& D, const ColK& c, double Z, int n)
     return lo - 2;
 }
 
-LT_DEV Wt make_weights2(const double* __restrict__ q, double xp, double yp, bool setinterp_quirk)
-{   // setInterp / interp weights (hydro:1706-1737, 2533-2565)
-    double x1 = q[0], x2 = q[1], x3 = q[2], x4 = q[3], y1 = q[4], y2 = q[5], y3 = q[6], y4 = q[7];
-    Wt w;
-    w.t = qdiv((xp - x1) * (y3 - y1) + (y1 - yp) * (x3 - x1), (x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1));
-    w.u = qdiv((xp - x1) * (y2 - y1) + (y1 - yp) * (x2 - x1), (x3 - x1) * (y2 - y1) - (y3 - y1) * (x2 - x1));
-    w.mode = 1;
-    if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
-        w.t = qdiv((xp - x3) * (y1 - y3) + (y3 - yp) * (x1 - x3), (x4 - x3) * (y1 - y3) - (y4 - y3) * (x1 - x3));
-        w.u = qdiv((xp - x3) * (y4 - y3) + (y3 - yp) * (x4 - x3), (x1 - x3) * (y4 - y3) - (y1 - y3) * (x4 - x3));
-        w.mode = 2;
-        if (w.t < 0. || w.u < 0. || (w.t + w.u) > 1.0) {
-            bool n1 = xp == x1 && yp == y1, n2 = xp == x2 && yp == y2, n3 = xp == x3 && yp == y3, n4 = xp == x4 && yp == y4;
-            if (n1 || n2 || n3 || n4) { if (!setinterp_quirk) w.mode = n4 ? 7 : n3 ? 6 : n2 ? 5 : 4; }
-            else w.mode = 3;
-        }
-    }
-    return w;
-}
-
 // Lagrange weights applied to DIFFERENCES from the centre value: like polintd, this
 // returns the data exactly when the three values are equal (a particle resting on the
 // bed must not drift by an ulp), and the weights need not sum to one in floating point.
@@ -204,9 +184,9 @@ LT_DEV void load_stencils(const LtDev& D, int re, int ue, int ve, Stage2& st)
 LT_DEV void stage_weights2(Stage2& s, double xp, double yp)
 {
     s.r.xp = s.u.xp = s.v.xp = xp; s.r.yp = s.u.yp = s.v.yp = yp;
-    s.r.w = make_weights2(s.r.q, xp, yp, false);
-    s.u.w = make_weights2(s.u.q, xp, yp, false);
-    s.v.w = make_weights2(s.v.q, xp, yp, false);
+    s.r.w = make_weights(s.r.q, xp, yp, false);
+    s.u.w = make_weights(s.u.q, xp, yp, false);
+    s.v.w = make_weights(s.v.q, xp, yp, false);
 }
 LT_DEV Rng make_rng(const LtDev& D, int n)
 {
@@ -215,6 +195,154 @@ LT_DEV Rng make_rng(const LtDev& D, int n)
     g.step = D.gstep; g.seed = (unsigned)D.P.seed;
     return g;
 }
+
+// ----------------------------------------------------------------- behave ---
+// behavior_module.f90:181-551.  Per-particle constants of initBehave (:118-131) are
+// uniform in v.2b, so P_swim(n,3) is a pure function of age.
+struct BehavOut { double X, Y, Z; bool bott; };
+template <class T>
+LT_DEVN BehavOut behave(const LtDev& D, int n, const Stage2& s0, const ColK& col, const Rng& g, double Zpar,
+                        double P_zb, double P_zc, double P_zf, double P_zetac, double P_age, double P_depth,
+                        double P_U, double P_V, double P_angle)
+{
+    const ltgpu_params& P = D.P;
+    BehavOut o; o.X = 0.0; o.Y = 0.0; o.Z = 0.0; o.bott = false;
+    double swim1 = (P.swimfast - P.swimslow) / (P.pediage - P.swimstart);
+    double swim2 = P.swimfast - swim1 * P.pediage;
+    double swim3 = 0.0;
+    if (P_age >= P.swimstart) swim3 = swim1 * P_age + swim2;
+    if (P_age >= P.pediage) swim3 = P.swimfast;
+    int bh = D.behave[n];
+    double timer = 0.0;
+    if (bh == 4 || bh == 5) {
+        if (P_age >= P.pediage && P_age < P.deadage) bh = 2;
+        timer = fmax(0.0, D.timer[n] - (double)P.dt);                   // ledger 15
+        D.timer[n] = timer;
+        D.behave[n] = (int8_t)bh;
+    }
+    double P_S = 0.0;
+    if (bh == 4 || (bh == 5 && timer == 0.0) || bh == 7) {
+        int deplvl = level_window2<false>(D, col, Zpar, P.us);
+        const T* f1[1] = {(const T*)D.salt}; const Stencil* s1[1] = {&s0.r}; const int g1[1] = {G_RHO};
+        double o1[1];
+        wcts2<T, false, 1>(D, f1, s1, g1, s0.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o1);
+        P_S = o1[0];
+    }
+    uint4 rnd = philox(g, 0x80000000u);
+    unsigned rw[3] = { rnd.x, rnd.y, rnd.z }; int w = 0;
+    double parBehav = 0.0, negpos, dev1, devB, sw;
+    const double f080 = (double)0.80f, f020 = (double)0.20f;
+    auto rand_swim = [&](double swv) {          // dev1 / switch / devB pattern
+        negpos = 1.0; dev1 = u_real1(rw[w++]);
+        if (dev1 > swv) negpos = -1.0;
+        devB = u_real1(rw[w++]);
+        parBehav = negpos * devB * swim3;
+    };
+    if (bh == 1) { if (P_zc < (P_zetac - 1.0)) rand_swim(f080); else rand_swim(0.5); }
+    if (bh == 2 || (bh == 5 && timer > 0.0)) { if (P_zc > (P_depth + 1.0)) rand_swim(f020); else rand_swim(0.5); }
+    if (bh == 3) {
+        double daytime = D.ix[2] / 86400.0;
+        double dtime = (daytime - trunc(daytime)) * 24.0, E0 = 0.0;
+        if (dtime > P.twistart && dtime < P.twiend) {
+            double tst = (dtime - P.twistart) * 3600.0;
+            double sn = sin(P.PI * tst / (P.daylength * 3600.0));
+            E0 = P.Em * sn * sn;
+        }
+        double P_light = E0 * exp(P.Kd * P_zc);
+        if (P_light < P.thresh) rand_swim(0.5);
+        if (P_light > P.thresh) rand_swim(f020);
+    }
+    if (bh == 4 || (bh == 5 && timer == 0.0)) {
+        double sprev = D.sprev[n], zprev = D.zprev[n];
+        if (D.it == 1) { sprev = P_S; zprev = P_zc; }
+        int btest = 0; double Sslope = 0.0;
+        double deltaS = sprev - P_S, deltaz = zprev - P_zc;
+        if (D.it > 1) Sslope = deltaS / deltaz;
+        if (bh == 4) {
+            if (fabs(Sslope) > P.Sgradient) {
+                negpos = 1.0; dev1 = u_real1(rw[w++]);
+                if (dev1 > f080) negpos = -1.0;
+                parBehav = negpos * swim3; btest = 1;
+            }
+            if (btest == 0) {
+                negpos = 1.0; dev1 = u_real1(rw[w++]);
+                if (P_age < 1.5 * 24. * 3600.) sw = (double)0.1f;
+                else if (P_age < 5. * 24. * 3600.) sw = (double)0.49f;
+                else if (P_age < 8. * 24. * 3600.) sw = (double)0.50f;
+                else {
+                    double ss = ((double)0.50f - (double)0.517f) / (8.0 * 24.0 * 3600.0 - P.pediage);
+                    sw = ss * P_age + (double)0.50f - ss * 8.0 * 24.0 * 3600.0;
+                    if (P_zc < P_depth + 1.) sw = 0.5;
+                }
+                if (dev1 > (1 - sw)) negpos = -1.0;
+                devB = u_real1(rw[w++]); parBehav = negpos * devB * swim3;
+            }
+        } else {
+            if (fabs(Sslope) > P.Sgradient) {
+                negpos = 1.0; dev1 = u_real1(rw[w++]); btest = 1;
+                timer = 2.0 * 3600.0;
+                if (dev1 > f020) negpos = -1.0;
+                parBehav = negpos * swim3;
+                if (P_age < 3.5 * 24. * 3600.) { btest = 0; timer = 0.; }
+                D.timer[n] = timer;
+            }
+            if (btest == 0) {
+                negpos = 1.0; dev1 = u_real1(rw[w++]); sw = (double)0.495f;
+                if (P_age < 1.5 * 24. * 3600.) sw = (double)0.9f;
+                if (P_age > 2.0 * 24. * 3600. && P_age < 3.5 * 24. * 3600.) {
+                    double ss = ((double)0.3f - (double)0.495f) / (2.0 * 24.0 * 3600.0 - 3.5 * 24.0 * 3600.0);
+                    sw = ss * P_age + (double)0.3f - ss * 2.0 * 24.0 * 3600.0;
+                }
+                if (dev1 > sw) negpos = -1.0;
+                devB = u_real1(rw[w++]); parBehav = negpos * devB * swim3;
+            }
+        }
+        D.sprev[n] = P_S; D.zprev[n] = P_zc;
+    }
+    if (bh == 6) parBehav = (P_age >= P.swimstart) ? P.sink : swim3;
+    o.Z = parBehav * P.idt;
+    if (bh == 7) {
+        double sprev = D.sprev[n];
+        if (D.it == 1) { sprev = P_S; D.sprev[n] = P_S; }
+        double ca = cos(P_angle), sa = sin(P_angle);
+        double X = (P_U * ca - P_V * sa), Y = (P_U * sa + P_V * ca);
+        double currentspeed = sqrt(X * X + Y * Y);
+        uint8_t fl = D.flags[n];
+        if (fl & LT_F_BOTTOM) {
+            if (sprev < P_S) { fl &= ~LT_F_BOTTOM; o.Z = P_depth + P.Swimdepth; }
+            else o.Z = -9999;
+        } else {
+            if (currentspeed > (double)0.05f) {
+                double Hd = P.Hswimspeed * P.idt;
+                double theta = atan(Y / X);
+                if (X > 0.0) { o.X = Hd * cos(theta); o.Y = Hd * sin(theta); }
+                if (X < 0.0) { o.X = -1.0 * Hd * cos(theta); o.Y = -1.0 * Hd * sin(theta); }
+                if (X == 0 && Y >= 0.0) { o.X = 0.0; o.Y = Hd; }
+                if (X == 0 && Y <= 0.0) { o.X = 0.0; o.Y = -1.0 * Hd; }
+                o.Z = P_depth + P.Swimdepth;
+            } else { o.Z = -9999; fl |= LT_F_BOTTOM; }
+        }
+        D.flags[n] = fl;
+        o.bott = (fl & LT_F_BOTTOM) != 0;
+    }
+    return o;
+}
+
+// ------------------------------------------------------------ error sites ---
+// The four check sites of update_particles share this (LTRANS.f90:834-879 etc.).
+// Returns nothing: the caller `cycle`s afterwards.
+LT_DEV void particle_error(const LtDev& D, int n, int code, double revertZ)
+{
+    int EF = D.P.ErrorFlag;
+    int gid = (int)(D.first_id + n);
+    if (EF < 1 || EF > 3) atomicMin(D.bad, gid);                         // STOP: lowest id wins
+    else if (EF == 1) D.z[n] = revertZ;                                  // pn = p (x, y unchanged)
+    else if (EF == 2) D.flags[n] |= LT_F_DEAD;
+    else D.flags[n] |= LT_F_OOB;
+    int k = atomicAdd(D.nev, 1);
+    if (k < D.evcap) { D.ev[k].particle = gid; D.ev[k].code = code; D.ev[k].time = D.ix[2]; }
+}
+
 
 // ============================================================ kernel 1: advect ==
 template <class T>
@@ -251,7 +379,7 @@ LT_DEV void advect_particle(const LtDev& D, int n)
     }
     Stage2 st;
     load_stencils(D, re, ue, ve, st);
-    Stencil s0 = st.r; s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights2(st.r.q, Xpar, Ypar, true);    // setInterp :882
+    Stencil s0 = st.r; s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights(st.r.q, Xpar, Ypar, true);    // setInterp :882
     const double P_depth = -1.0 * gather_static(D, D.depth, s0);         // :892-896
     const double P_angle = gather_static(D, D.angle, s0);
     double P_zetab, P_zetac, P_zetaf;
@@ -318,98 +446,97 @@ LT_DEV void advect_particle(const LtDev& D, int n)
 }
 
 // ============================================================= kernel 2: VTurb ==
+// ver_turb_module.f90:30-380.  Everything a warp does here is arranged to be CONVERGENT:
+//   1. the KH profile (ws levels x 3 times) and the w-level depths are gathered once into
+//      thread-local arrays (21 iterations, identical for every lane);
+//   2. knot values fy(k), knot slopes yp(k) (YPC1) and tension factors sg(k) (SIGS) are built
+//      for a window of VW knots around the particle in lock-step loops;
+//   3. the 60 random-displacement sub-steps then only look knots up.
+// A particle that walks out of its window rebuilds it around the new position (rare: the
+// window spans ~ +-15 knots = +-18% of the water column, the RDM step is ~1%).
 #define VW 32                      // knots held per window
-struct Lin { int lev; double slope, icpt, znext; };   // current KH segment of one time level
 
 template <class T>
 struct VtCtx {
-    const LtDev& D; const Stencil& s; const ColK& col; const T* fk;
+    const LtDev& D;
     int ws, p2;
-    double z1[3], zN[3], hs[3];           // w-level 1 / ws and newx spacing, per hydro time
-    double kh1[3], khN[3];                // KH at the bottom / top w-level
+    double khp[3][LT_MAXLEV];             // KH at the particle, per hydro time and w-level (:102-108)
+    double zl[3][LT_MAXLEV];              // w-level depths at the particle
+    double hs[3];                         // newx spacing per hydro time (:120-124)
     double Z1, ZN, H, rH;                 // time-combined knot line: x(k) = Z1 + (k - 0.5) H
-    double fy[VW]; int ka, kb;            // knot values in the window [ka, kb] (1-based)
-    LT_DEV VtCtx(const LtDev& D_, const Stencil& s_, const ColK& c_) : D(D_), s(s_), col(c_), fk((const T*)D_.kh) {}
+    double fy[VW], yp[VW], sg[VW];        // knot value, YPC1 slope, SIGS tension of interval (k, k+1)
+    int ka, kb, ia, ib;                   // knots [ka, kb] held; intervals [ia, ib] fully defined
+    bool sigerr;
+    LT_DEV VtCtx(const LtDev& D_) : D(D_) {}
 
-    LT_DEV double zeta(int t) const { return t == 0 ? col.zb : (t == 1 ? col.zc : col.zf); }
-    LT_DEV double wz(int t, int l) const { return zlev2(D, col, zeta(t), D.SCW[l], D.CSW[l]); }   // l 0-based
-    LT_DEV double kh(int t, int l) const
-    {
-        double b, c, f; gather_bcf<T>(D, fk, ws, l, s, G_RHO, s.nd, b, c, f);
-        return t == 0 ? b : (t == 1 ? c : f);
-    }
     LT_DEV double knot_x(int k) const { return k <= 1 ? Z1 : (k >= p2 ? ZN : Z1 + ((double)k - 0.5) * H); }
-    // newx(j) of ver_turb:120-124
-    LT_DEV double newx(int t, int j) const { return z1[t] + (double)(j - 4) * hs[t]; }
-    // segment of the KH profile containing x: smallest jlo >= 1 with wz(jlo+1) > x (:135-166)
-    LT_DEV void seg_set(Lin& L, int t, int lev) const
-    {   // lev = jlo (1-based)
-        double zl = wz(t, lev - 1), zh = wz(t, lev), kl = kh(t, lev - 1), khh = kh(t, lev);
-        L.lev = lev; L.slope = qdiv(kl - khh, zl - zh); L.icpt = kl - L.slope * zl; L.znext = zh;   // :126-133
-    }
-    LT_DEV void seg_init(Lin& L, int t, double x) const
+    LT_DEV double newx(int t, int j) const { return zl[t][0] + (double)(j - 4) * hs[t]; }
+    // piecewise-linear KH profile at newx(j): smallest jlo >= 1 with wz(jlo+1) > x (:135-166), pads (:169-177)
+    LT_DEV double newy(int t, int j, int& lev) const
     {
-        int lo = 1, hi = ws - 1;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (wz(t, mid) > x) hi = mid; else lo = mid + 1; }
-        seg_set(L, t, lo);
-    }
-    LT_DEV double newy(Lin& L, int t, int j) const
-    {   // :135-177 incl. the pads (ledger 11: the bottom pad is KHb(1) for all three times)
-        if (j <= 4) return kh1[0];
-        if (j >= p2 + 4) return khN[t];
+        if (j <= 4) return khp[0][0];                                  // ledger 11: KHb(1) for all three times
+        if (j >= p2 + 4) return khp[t][ws - 1];
         double x = newx(t, j);
-        while (!(L.znext > x) && L.lev < ws - 1) seg_set(L, t, L.lev + 1);
-        return L.slope * x + L.icpt;
+        while (!(zl[t][lev] > x) && lev < ws - 1) ++lev;               // lev = jlo (1-based) -> zl[lev] is wz(jlo+1)
+        double zlo = zl[t][lev - 1], zhi = zl[t][lev], klo = khp[t][lev - 1], khi = khp[t][lev];
+        double slope = qdiv(klo - khi, zlo - zhi);                     // :126-133
+        return slope * x + (klo - slope * zlo);
     }
-    // knot values fy(k), k in [ka_, ka_ + VW - 1] /\ [1, p2] (:184-275)
+    // knot values, slopes and tension factors for knots [ka_, ka_ + VW - 1] /\ [1, p2]
     LT_DEVN void build(int ka_)
     {
         ka = ka_; kb = min(p2, ka + VW - 1);
-        int k0 = max(ka, 2), k1 = min(kb, p2 - 1);
-        double S[3]; Lin hi[3], lo[3];
+        const int k0 = max(ka, 2), k1 = min(kb, p2 - 1);
+        double S[3] = {0.0, 0.0, 0.0}; int hi[3] = {1, 1, 1}, lo[3] = {1, 1, 1};
         if (k0 <= k1) {
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-                double x0 = newx(t, max(k0, 5));
-                seg_init(lo[t], t, x0); hi[t] = lo[t];
                 double acc = 0.0;
-                for (int j = k0; j <= k0 + 7; ++j) acc += newy(hi[t], t, j);
+                for (int j = k0; j <= k0 + 7; ++j) acc += newy(t, j, hi[t]);       // :184-194
                 S[t] = acc;
+                double d = newy(t, k0, lo[t]); (void)d;                             // position the trailing pointer
             }
         }
         for (int k = ka; k <= kb; ++k) {
             double my[3];
-            if (k == 1) { my[0] = kh1[0]; my[1] = kh1[1]; my[2] = kh1[2]; }
-            else if (k == p2) { my[0] = khN[0]; my[1] = khN[1]; my[2] = khN[2]; }
+            if (k == 1) { my[0] = khp[0][0]; my[1] = khp[1][0]; my[2] = khp[2][0]; }                      // :197-210
+            else if (k == p2) { my[0] = khp[0][ws - 1]; my[1] = khp[1][ws - 1]; my[2] = khp[2][ws - 1]; }
             else {
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
-                    if (k > k0) S[t] += newy(hi[t], t, k + 7) - newy(lo[t], t, k - 1);
+                    if (k > k0) S[t] += newy(t, k + 7, hi[t]) - newy(t, k - 1, lo[t]);   // running 8-point sum
                     my[t] = S[t] / 8.0;
                 }
             }
             double fb = lag(D.LW[0], my[0], my[1], my[2]), fc = lag(D.LW[1], my[0], my[1], my[2]), ff = lag(D.LW[2], my[0], my[1], my[2]);
-            fb = fb < 0.0 ? 0.0 : fb; fc = fc < 0.0 ? 0.0 : fc; ff = ff < 0.0 ? 0.0 : ff;
-            fy[k - ka] = (fb + 4.0 * fc + ff) / 6.0;
+            fb = fb < 0.0 ? 0.0 : fb; fc = fc < 0.0 ? 0.0 : fc; ff = ff < 0.0 ? 0.0 : ff;     // :264-268
+            fy[k - ka] = (fb + 4.0 * fc + ff) / 6.0;                                          // :272-275
         }
-    }
-    LT_DEV bool have(int k) const { return k >= ka && k <= kb; }
-    LT_DEV double Y(int k) const { return fy[k - ka]; }
-    // YPC1 slope at knot k (tension:852-978), needs Y(k-1..k+1)
-    LT_DEV double yp(int k) const
-    {
-        if (k == 1) {
-            double d1 = knot_x(2) - knot_x(1), d2 = knot_x(3) - knot_x(2);
-            double s1 = qdiv(Y(2) - Y(1), d1), s2 = qdiv(Y(3) - Y(2), d2);
-            return ypc1_end(s1, s1 + qdiv(d1 * (s1 - s2), d1 + d2));
+        // YPC1 (tension:852-978): needs both neighbours, or the profile end
+        const int pa = ka == 1 ? 1 : ka + 1, pb = kb == p2 ? p2 : kb - 1;
+        for (int k = pa; k <= pb; ++k) {
+            double v;
+            if (k == 1) {
+                double d1 = knot_x(2) - knot_x(1), d2 = knot_x(3) - knot_x(2);
+                double s1 = qdiv(fy[2 - ka] - fy[1 - ka], d1), s2 = qdiv(fy[3 - ka] - fy[2 - ka], d2);
+                v = ypc1_end(s1, s1 + qdiv(d1 * (s1 - s2), d1 + d2));
+            } else if (k == p2) {
+                double d1 = knot_x(p2 - 1) - knot_x(p2 - 2), d2 = knot_x(p2) - knot_x(p2 - 1);
+                double s1 = qdiv(fy[p2 - 1 - ka] - fy[p2 - 2 - ka], d1), s2 = qdiv(fy[p2 - ka] - fy[p2 - 1 - ka], d2);
+                v = ypc1_end(s2, s2 + qdiv(d2 * (s2 - s1), d1 + d2));
+            } else {
+                double d1 = knot_x(k) - knot_x(k - 1), d2 = knot_x(k + 1) - knot_x(k);
+                v = ypc1_mid(d1, d2, qdiv(fy[k - ka] - fy[k - 1 - ka], d1), qdiv(fy[k + 1 - ka] - fy[k - ka], d2));
+            }
+            yp[k - ka] = v;
         }
-        if (k == p2) {
-            double d1 = knot_x(p2 - 1) - knot_x(p2 - 2), d2 = knot_x(p2) - knot_x(p2 - 1);
-            double s1 = qdiv(Y(p2 - 1) - Y(p2 - 2), d1), s2 = qdiv(Y(p2) - Y(p2 - 1), d2);
-            return ypc1_end(s2, s2 + qdiv(d2 * (s2 - s1), d1 + d2));
+        // SIGS (tension:314-782) for every interval with both slopes known
+        ia = pa; ib = pb - 1;
+        for (int k = ia; k <= ib; ++k) {
+            int e = 0;
+            sg[k - ka] = sigs_interval(knot_x(k + 1) - knot_x(k), fy[k - ka], fy[k + 1 - ka], yp[k - ka], yp[k + 1 - ka], e);
+            if (e) sigerr = true;
         }
-        double d1 = knot_x(k) - knot_x(k - 1), d2 = knot_x(k + 1) - knot_x(k);
-        return ypc1_mid(d1, d2, qdiv(Y(k) - Y(k - 1), d1), qdiv(Y(k + 1) - Y(k), d2));
     }
     // HVAL / HPVAL interval choice incl. INTRVL (tension:1026-1041, 1287-1354)
     LT_DEV int interval(double Tq) const
@@ -422,22 +549,8 @@ struct VtCtx {
         while (k < p2 - 1 && !(Tq < knot_x(k + 1))) ++k;
         return k;
     }
+    LT_DEV void need(int I) { if (I < ia || I > ib) build(max(1, min(I - VW / 2 + 1, p2 - VW + 1))); }
 };
-
-struct IvCache { int I; double X1, X2, Y1, Y2, P1, P2, SG; int err; };
-
-template <class T>
-LT_DEV void vt_interval(VtCtx<T>& V, IvCache& c, int I)
-{
-    if (c.I == I) return;
-    int need_lo = max(1, I - 1), need_hi = min(V.p2, I + 2);
-    if (!(V.have(need_lo) && V.have(need_hi)))
-        V.build(max(1, min(I - VW / 2 + 1, V.p2 - VW + 1)));
-    c.I = I; c.X1 = V.knot_x(I); c.X2 = V.knot_x(I + 1); c.Y1 = V.Y(I); c.Y2 = V.Y(I + 1);
-    c.P1 = V.yp(I); c.P2 = V.yp(I + 1);
-    c.err = 0;
-    c.SG = sigs_interval(c.X2 - c.X1, c.Y1, c.Y2, c.P1, c.P2, c.err);
-}
 
 template <class T>
 LT_DEV void vturb_particle(const LtDev& D, int n)
@@ -447,24 +560,24 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     const double Xpar = D.x[n], Ypar = D.y[n];
     const int re = D.r_ele[n];
     Stencil s0; s0.q = D.R.ele + (size_t)(re - 1) * 8; s0.nd = __ldg(D.R.node + (re - 1));
-    s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights2(s0.q, Xpar, Ypar, true);     // getInterp uses setInterp's weights
+    s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights(s0.q, Xpar, Ypar, true);      // getInterp uses setInterp's weights
     ColK col; col.zb = D.s_zeb[n]; col.zc = D.s_zec[n]; col.zf = D.s_zef[n]; col.depth = D.s_depth[n]; col.h = -1.0 * col.depth;
     const double P_zc = D.s_pzc[n], P_depth = col.depth, P_zetac = col.zc;
-    VtCtx<T> V(D, s0, col);
-    V.ws = D.P.ws; V.p2 = 4 * V.ws;
+    VtCtx<T> V(D);
+    V.ws = D.P.ws; V.p2 = 4 * V.ws; V.sigerr = false;
+    const T* fk = (const T*)D.kh;
+#pragma unroll 1
+    for (int l = 0; l < V.ws; ++l) {
+        gather_bcf<T>(D, fk, V.ws, l, s0, G_RHO, s0.nd, V.khp[0][l], V.khp[1][l], V.khp[2][l]);
+        zlev3<true>(D, col, l, V.zl[0][l], V.zl[1][l], V.zl[2][l]);
+    }
     const double rp2 = 1.0 / (double)V.p2;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        V.z1[t] = V.wz(t, 0); V.zN[t] = V.wz(t, V.ws - 1);
-        V.hs[t] = (V.zN[t] - V.z1[t]) * rp2;
-    }
-    gather_bcf<T>(D, V.fk, V.ws, 0, s0, G_RHO, s0.nd, V.kh1[0], V.kh1[1], V.kh1[2]);
-    gather_bcf<T>(D, V.fk, V.ws, V.ws - 1, s0, G_RHO, s0.nd, V.khN[0], V.khN[1], V.khN[2]);
-    V.Z1 = lag(D.LW4, V.z1[0], V.z1[1], V.z1[2]);
-    V.ZN = lag(D.LW4, V.zN[0], V.zN[1], V.zN[2]);
+    for (int t = 0; t < 3; ++t) V.hs[t] = (V.zl[t][V.ws - 1] - V.zl[t][0]) * rp2;
+    V.Z1 = lag(D.LW4, V.zl[0][0], V.zl[1][0], V.zl[2][0]);
+    V.ZN = lag(D.LW4, V.zl[0][V.ws - 1], V.zl[1][V.ws - 1], V.zl[2][V.ws - 1]);
     V.H = (V.ZN - V.Z1) * rp2; V.rH = qrcp(V.H);
-    V.ka = 1; V.kb = 0;
-    IvCache c; c.I = -1;
+    V.ka = 1; V.kb = 0; V.ia = 1; V.ib = 0;
     const Rng g = make_rng(D, n);
     const double deltat = 2.0;
     const int loop = D.P.idt / 2;                                       // :282-283
@@ -474,18 +587,20 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     for (int i = 0; i < loop; ++i) {                                    // :291-337
         double Kprimec = 0.0;
         if (!(ParZc < P_depth || ParZc > P_zetac)) {
-            vt_interval(V, c, V.interval(ParZc));
-            if (!c.err) Kprimec = hpval_interval(ParZc, c.X1, c.X2, c.Y1, c.Y2, c.P1, c.P2, c.SG);
-            else Kprimec = qdiv(c.Y1 - c.Y2, c.X1 - c.X2);              // linint slope
+            int I = V.interval(ParZc); V.need(I);
+            int q = I - V.ka;
+            if (!V.sigerr) Kprimec = hpval_interval(ParZc, V.knot_x(I), V.knot_x(I + 1), V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
+            else Kprimec = qdiv(V.fy[q] - V.fy[q + 1], V.knot_x(I) - V.knot_x(I + 1));       // linint slope
         }
         const double KprimeZc = -1.0 * Kprimec * deltat;
         const double Z3rdc = ParZc + 0.5 * KprimeZc;
         double KH3rdc;
         if (Z3rdc < P_depth || Z3rdc > P_zetac) KH3rdc = background;
         else {
-            vt_interval(V, c, V.interval(Z3rdc));
-            if (!c.err) KH3rdc = hval_interval(Z3rdc, c.X1, c.X2, c.Y1, c.Y2, c.P1, c.P2, c.SG);
-            else { double m = qdiv(c.Y1 - c.Y2, c.X1 - c.X2); KH3rdc = m * Z3rdc + (c.Y1 - m * c.X1); }
+            int I = V.interval(Z3rdc); V.need(I);
+            int q = I - V.ka;
+            if (!V.sigerr) KH3rdc = hval_interval(Z3rdc, V.knot_x(I), V.knot_x(I + 1), V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
+            else { double m = qdiv(V.fy[q] - V.fy[q + 1], V.knot_x(I) - V.knot_x(I + 1)); KH3rdc = m * Z3rdc + (V.fy[q] - m * V.knot_x(I)); }
             if (KH3rdc < background) KH3rdc = background;
         }
         if ((i & 1) == 0) rnd = philox(g, 1u + (unsigned)(i >> 1));
@@ -631,11 +746,11 @@ LT_DEV void finish_particle(const LtDev& D, int n)
     int re = D.r_ele[n], ue = D.u_ele[n], ve = D.v_ele[n];
     BehavOut bo; bo.X = bo.Y = bo.Z = 0.0; bo.bott = false;
     if (P.Behavior != 0) {                                               // :1110
-        Stage st; Column col;
+        Stage2 st; ColK col;
         st.r.q = D.R.ele + (size_t)(re - 1) * 8; st.r.nd = __ldg(D.R.node + (re - 1));
         st.u.nd = __ldg(D.U.node + (ue - 1));
         st.r.xp = Xpar; st.r.yp = Ypar; st.r.w = make_weights(st.r.q, Xpar, Ypar, false);
-        col.zb = D.s_zeb[n]; col.zc = P_zetac; col.zf = D.s_zef[n]; col.depth = P_depth;
+        col.zb = D.s_zeb[n]; col.zc = P_zetac; col.zf = D.s_zef[n]; col.depth = P_depth; col.h = -1.0 * P_depth;
         bo = behave<T>(D, n, st, col, make_rng(D, n), Zpar, D.s_pzb[n], D.s_pzc[n], D.s_pzf[n], P_zetac, age, P_depth,
                        D.s_pu[n], D.s_pv[n], D.s_angle[n]);
     }

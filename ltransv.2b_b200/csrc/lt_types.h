@@ -50,17 +50,15 @@ struct LtDev {
     int n; long long first_id;
     // events
     ltgpu_event* ev; int* nev; int evcap; int* bad;
-    // VTurb scratch (v1 kernel): 7 arrays, element k of thread t at [k*vt_stride + t]
-    double* vt; long long vt_stride; int vt_p2;
-    // v2: per-particle scratch passed between the three step kernels (SoA)
+    // per-particle scratch passed between the three step kernels (SoA)
     double *s_depth, *s_angle, *s_zeb, *s_zec, *s_zef, *s_pzb, *s_pzc, *s_pzf, *s_zpar,
            *s_nx, *s_ny, *s_advz, *s_pu, *s_pv, *s_turbv;
     uint8_t* s_act;
-    // v2: Lagrange form of the 3-point time polynomial (interpolation_module.f90:70-107),
+    // Lagrange form of the 3-point time polynomial (interpolation_module.f90:70-107),
     // LW[v][t] = weight of hydro record t (b,c,f) at internal time ix(v), with the p == 1
     // triplet (b,b,c) folded in; LW4 = (LW[0] + 4 LW[1] + LW[2]) / 6; LWz = raw weights at ix(2)
     double LW[3][3], LW4[3], LWz[3];
-    // v2: exact spatial indices over the boundary tables (built by set_bounds)
+    // exact spatial indices over the boundary tables (built by set_bounds)
     double sg_x0, sg_y0, sg_rcs; int sg_nx, sg_ny; const int *sg_ptr, *sg_idx;     // segment buckets
     double mb_y0, mb_rbh; int mb_n; const int *mb_ptr, *mb_idx;                     // main polygon y-bands
     double ib_y0, ib_rbh; int ib_n; const int *ib_ptr, *ib_idx; int ib_ok;          // island y-bands

@@ -13,18 +13,9 @@
 #include <algorithm>
 #include <string>
 #include <vector>
-#include "lt_step.cuh"
 #include "lt_step2.cuh"
 
 // ------------------------------------------------------------------ kernels --
-template <class T>
-__global__ void __launch_bounds__(128) k_step(const __grid_constant__ LtDev D)
-{
-    size_t tslot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t n = tslot; n < (size_t)D.n; n += stride) step_particle<T>(D, (int)n, tslot);
-}
-
 template <class T>
 __global__ void __launch_bounds__(128) k_advect(const __grid_constant__ LtDev D)
 {
@@ -140,7 +131,6 @@ struct ltgpu_ctx {
     std::string err;
     bool have_grid = false, have_bounds = false, have_particles = false, have_habitat = false;
     int nthreads_grid = 0;
-    bool v1 = false;                         // LTGPU_KERNEL=v1: the fused first-generation kernel (A/B checks)
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -317,8 +307,6 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming);
     cudaEventCreate(&ctx->t0); cudaEventCreate(&ctx->t1);
     ctx->D.sb = 0; ctx->D.sc = 1; ctx->D.sf = 2; ctx->spare = 3;
-    const char* kv = getenv("LTGPU_KERNEL");
-    ctx->v1 = kv && strcmp(kv, "v1") == 0;
     *out = ctx;
     return LTGPU_OK;
 }
@@ -528,13 +516,6 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
                      &D.s_nx, &D.s_ny, &D.s_advz, &D.s_pu, &D.s_pv, &D.s_turbv};
     for (auto p : sc) TRY(dalloc(ctx, p, N));
     TRY(dalloc(ctx, &D.s_act, N));
-    // v1 VTurb scratch: 7 arrays of (4*ws + 8) doubles per resident thread
-    int threads = (int)std::min<size_t>((size_t)ctx->nthreads_grid, ((N + 127) / 128) * 128);
-    ctx->nthreads_grid = threads;
-    if (ctx->prm.VTurbOn && ctx->v1) {
-        D.vt_p2 = 4 * ctx->prm.ws; D.vt_stride = threads;
-        TRY(dalloc(ctx, &D.vt, (size_t)7 * (D.vt_p2 + 8) * (size_t)threads));
-    }
     CK(cudaStreamSynchronize(ctx->compute));
     ctx->have_particles = true;
     return LTGPU_OK;
@@ -626,12 +607,7 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
         }
         for (int t = 0; t < 3; ++t) D.LW4[t] = (D.LW[0][t] + 4.0 * D.LW[1][t] + D.LW[2][t]) / 6.0;
     }
-    if (ctx->v1) {
-        int blocks = ctx->nthreads_grid / 128;
-        if (ctx->esz == 4) k_step<float><<<blocks, 128, 0, ctx->compute>>>(D);
-        else k_step<double><<<blocks, 128, 0, ctx->compute>>>(D);
-        ctx->launches++;
-    } else {
+    {
         int blocks = (D.n + 127) / 128;
         if (ctx->esz == 4) {
             k_advect<float><<<blocks, 128, 0, ctx->compute>>>(D);
