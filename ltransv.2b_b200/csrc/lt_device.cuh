@@ -44,28 +44,36 @@ LT_DEV double qdiv(double a, double b)
 #define kF32_1em6 0.000001f     // DBLE(0.000001) likewise                     (LTRANS.f90:1002)
 
 // ---------------------------------------------------------------- fields ----
-template <class T>
-LT_DEV void load_bcf(const T* base, size_t idx, int sb, int sc, int sf, double& b, double& c, double& f);
-
-LT_DEV double sel4(double a0, double a1, double a2, double a3, int s)
+// One (node, level) of a hydro field = 4 ring slots in one 16-byte (f32) / 32-byte (f64)
+// chunk.  The back / centre / forward records sit in slots PH, PH+1, PH+2 (mod 4), the
+// fourth being refilled; PH is a template parameter so the component pick costs nothing
+// (a run-time pick cost 13% of k_advect's instructions, profiles/r01_notes.md).
+template <int PH> LT_DEV void pick3(double a0, double a1, double a2, double a3, double& b, double& c, double& f)
 {
-    double lo = (s & 1) ? a1 : a0, hi = (s & 1) ? a3 : a2;
-    return (s & 2) ? hi : lo;
+    if (PH == 0) { b = a0; c = a1; f = a2; }
+    else if (PH == 1) { b = a1; c = a2; f = a3; }
+    else if (PH == 2) { b = a2; c = a3; f = a0; }
+    else { b = a3; c = a0; f = a1; }
 }
-template <>
-LT_DEV void load_bcf<float>(const float* base, size_t idx, int sb, int sc, int sf, double& b, double& c, double& f)
-{
-    float4 q = __ldg(reinterpret_cast<const float4*>(base) + idx);
-    double a0 = (double)q.x, a1 = (double)q.y, a2 = (double)q.z, a3 = (double)q.w;
-    b = sel4(a0, a1, a2, a3, sb); c = sel4(a0, a1, a2, a3, sc); f = sel4(a0, a1, a2, a3, sf);
-}
-template <>
-LT_DEV void load_bcf<double>(const double* base, size_t idx, int sb, int sc, int sf, double& b, double& c, double& f)
-{
-    const double2* p = reinterpret_cast<const double2*>(base) + 2 * idx;
-    double2 lo = __ldg(p), hi = __ldg(p + 1);
-    b = sel4(lo.x, lo.y, hi.x, hi.y, sb); c = sel4(lo.x, lo.y, hi.x, hi.y, sc); f = sel4(lo.x, lo.y, hi.x, hi.y, sf);
-}
+template <class T, int PH> struct LoadBCF;
+template <int PH> struct LoadBCF<float, PH> {
+    static LT_DEV void get(const float* base, size_t idx, double& b, double& c, double& f)
+    {
+        float4 q = __ldg(reinterpret_cast<const float4*>(base) + idx);
+        float fb, fc, ff;
+        if (PH == 0) { fb = q.x; fc = q.y; ff = q.z; } else if (PH == 1) { fb = q.y; fc = q.z; ff = q.w; }
+        else if (PH == 2) { fb = q.z; fc = q.w; ff = q.x; } else { fb = q.w; fc = q.x; ff = q.y; }
+        b = (double)fb; c = (double)fc; f = (double)ff;
+    }
+};
+template <int PH> struct LoadBCF<double, PH> {
+    static LT_DEV void get(const double* base, size_t idx, double& b, double& c, double& f)
+    {
+        const double2* p = reinterpret_cast<const double2*>(base) + 2 * idx;
+        double2 lo = __ldg(p), hi = __ldg(p + 1);
+        pick3<PH>(lo.x, lo.y, hi.x, hi.y, b, c, f);
+    }
+};
 
 // ------------------------------------------------------------- gridcell -----
 // gridcell_module.f90:26-257, single element.  q = x0..x3,y0..y3.
@@ -160,8 +168,11 @@ LT_DEV Wt make_weights(const double* __restrict__ q, double xp, double yp, bool 
 }
 LT_DEV double combine(const Wt& w, double v1, double v2, double v3, double v4)
 {
-    if (w.mode == 1) return v1 + (v2 - v1) * w.t + (v3 - v1) * w.u;
-    if (w.mode == 2) return v3 + (v4 - v3) * w.t + (v1 - v3) * w.u;
+    if (w.mode <= 2) {      // v1 + (v2-v1) t + (v3-v1) u   or   v3 + (v4-v3) t + (v1-v3) u, without diverging
+        const bool m2 = w.mode == 2;
+        const double o = m2 ? v3 : v1, a = m2 ? v4 : v2, b = m2 ? v1 : v3;
+        return o + (a - o) * w.t + (b - o) * w.u;
+    }
     if (w.mode == 3) return w.t * v1 + w.u * v2 + w.w2 * v3 + w.w3 * v4;
     return w.mode == 4 ? v1 : w.mode == 5 ? v2 : w.mode == 6 ? v3 : v4;
 }
@@ -199,15 +210,15 @@ struct Stencil {            // element corner nodes + coordinates + weights at o
 
 // value of one (field, level) at the three hydro times: the 4-corner gather of
 // getInterp (hydro:1743-2005) / interp (hydro:2008-2569) with precomputed weights.
-template <class T>
+template <class T, int PH>
 LT_DEV void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
                        double& rb, double& rc, double& rf)
 {
     double b[4], c[4], f[4];
-    load_bcf<T>(fld, (size_t)s.nd.x * L + lev0, D.sb, D.sc, D.sf, b[0], c[0], f[0]);
-    load_bcf<T>(fld, (size_t)s.nd.y * L + lev0, D.sb, D.sc, D.sf, b[1], c[1], f[1]);
-    load_bcf<T>(fld, (size_t)s.nd.z * L + lev0, D.sb, D.sc, D.sf, b[2], c[2], f[2]);
-    load_bcf<T>(fld, (size_t)s.nd.w * L + lev0, D.sb, D.sc, D.sf, b[3], c[3], f[3]);
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.x * L + lev0, b[0], c[0], f[0]);
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.y * L + lev0, b[1], c[1], f[1]);
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.z * L + lev0, b[2], c[2], f[2]);
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.w * L + lev0, b[3], c[3], f[3]);
     if (D.P.FreeSlip) {
         const uint8_t* mk = grid == G_RHO ? D.R.mask : grid == G_U ? D.U.mask : D.V.mask;
         int m[4] = { mk[s.nd.x], mk[s.nd.y], mk[s.nd.z], mk[s.nd.w] }, md[4];

@@ -103,7 +103,7 @@ struct Stage2 { Stencil r, u, v; };
 
 // WCTS_ITPI (hydro:2577-2689) for NF fields sharing one set of knots (u and v share the
 // rho-level knots).  v = 0,1,2: value at ix(v+1); v = 3: (b + 4c + f)/6.
-template <class T, bool W, int NF>
+template <class T, int PH, bool W, int NF>
 LT_DEV void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st, const int* grid, int4 und, int L,
                   const ColK& col, int deplvl, double P_zb, double P_zc, double P_zf, int v, double* out)
 {
@@ -114,7 +114,7 @@ LT_DEV void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st,
         int k = deplvl - 1 + i;
         zlev3<W>(D, col, k, kb.x[i], kc.x[i], kf.x[i]);
 #pragma unroll
-        for (int f = 0; f < NF; ++f) gather_bcf<T>(D, fld[f], L, k, *st[f], grid[f], und, vb[f][i], vc[f][i], vf[f][i]);
+        for (int f = 0; f < NF; ++f) gather_bcf<T, PH>(D, fld[f], L, k, *st[f], grid[f], und, vb[f][i], vc[f][i], vf[f][i]);
     }
     knots_prepare(kb); knots_prepare(kc);
     const bool first = D.p == 1;                     // (b,b,c): the forward profile is not used
@@ -130,7 +130,7 @@ LT_DEV void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st,
 }
 
 // find_currents (LTRANS.f90:1422-1614)
-template <class T>
+template <class T, int PH>
 LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, double Zpar,
                             double P_zb, double P_zc, double P_zf, int version,
                             double& Uad, double& Vad, double& Wad)
@@ -144,9 +144,9 @@ LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, do
     const double* lw = D.LW[version - 1];
     if (Zpar < zb1 || Zpar < zc1 || Zpar < zf1) {                      // log layer :1489-1600
         double Ub, Uc, Uf, Vb, Vc, Vf, Wb, Wc, Wf;
-        gather_bcf<T>(D, fu, us, 0, s.u, G_U, s.u.nd, Ub, Uc, Uf);
-        gather_bcf<T>(D, fv, us, 0, s.v, G_V, s.u.nd, Vb, Vc, Vf);
-        gather_bcf<T>(D, fw, ws, 1, s.r, G_RHO, s.u.nd, Wb, Wc, Wf);
+        gather_bcf<T, PH>(D, fu, us, 0, s.u, G_U, s.u.nd, Ub, Uc, Uf);
+        gather_bcf<T, PH>(D, fv, us, 0, s.v, G_V, s.u.nd, Vb, Vc, Vf);
+        gather_bcf<T, PH>(D, fw, ws, 1, s.r, G_RHO, s.u.nd, Wb, Wc, Wf);
         double rz0 = qrcp(z0);
         double num = log10((Zpar - wzb1) * rz0);
         double wzb2, wzc2, wzf2; zlev3<true>(D, col, 1, wzb2, wzc2, wzf2);
@@ -164,13 +164,13 @@ LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, do
     {
         const T* f2[2] = {fu, fv}; const Stencil* s2[2] = {&s.u, &s.v}; const int g2[2] = {G_U, G_V};
         double o[2];
-        wcts2<T, false, 2>(D, f2, s2, g2, s.u.nd, us, col, ii, P_zb, P_zc, P_zf, version - 1, o);
+        wcts2<T, PH, false, 2>(D, f2, s2, g2, s.u.nd, us, col, ii, P_zb, P_zc, P_zf, version - 1, o);
         Uad = o[0]; Vad = o[1];
     }
     {
         const T* f1[1] = {fw}; const Stencil* s1[1] = {&s.r}; const int g1[1] = {G_RHO};
         double o[1];
-        wcts2<T, true, 1>(D, f1, s1, g1, s.u.nd, ws, col, iii, P_zb, P_zc, P_zf, version - 1, o);
+        wcts2<T, PH, true, 1>(D, f1, s1, g1, s.u.nd, ws, col, iii, P_zb, P_zc, P_zf, version - 1, o);
         Wad = o[0];
     }
 }
@@ -200,7 +200,7 @@ LT_DEV Rng make_rng(const LtDev& D, int n)
 // behavior_module.f90:181-551.  Per-particle constants of initBehave (:118-131) are
 // uniform in v.2b, so P_swim(n,3) is a pure function of age.
 struct BehavOut { double X, Y, Z; bool bott; };
-template <class T>
+template <class T, int PH>
 LT_DEVN BehavOut behave(const LtDev& D, int n, const Stage2& s0, const ColK& col, const Rng& g, double Zpar,
                         double P_zb, double P_zc, double P_zf, double P_zetac, double P_age, double P_depth,
                         double P_U, double P_V, double P_angle)
@@ -225,7 +225,7 @@ LT_DEVN BehavOut behave(const LtDev& D, int n, const Stage2& s0, const ColK& col
         int deplvl = level_window2<false>(D, col, Zpar, P.us);
         const T* f1[1] = {(const T*)D.salt}; const Stencil* s1[1] = {&s0.r}; const int g1[1] = {G_RHO};
         double o1[1];
-        wcts2<T, false, 1>(D, f1, s1, g1, s0.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o1);
+        wcts2<T, PH, false, 1>(D, f1, s1, g1, s0.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o1);
         P_S = o1[0];
     }
     uint4 rnd = philox(g, 0x80000000u);
@@ -345,7 +345,7 @@ LT_DEV void particle_error(const LtDev& D, int n, int code, double revertZ)
 
 
 // ============================================================ kernel 1: advect ==
-template <class T>
+template <class T, int PH>
 LT_DEV void advect_particle(const LtDev& D, int n)
 {
     const ltgpu_params& P = D.P;
@@ -383,7 +383,7 @@ LT_DEV void advect_particle(const LtDev& D, int n)
     const double P_depth = -1.0 * gather_static(D, D.depth, s0);         // :892-896
     const double P_angle = gather_static(D, D.angle, s0);
     double P_zetab, P_zetac, P_zetaf;
-    gather_bcf<T>(D, (const T*)D.zeta, 1, 0, s0, G_RHO, s0.nd, P_zetab, P_zetac, P_zetaf);
+    gather_bcf<T, PH>(D, (const T*)D.zeta, 1, 0, s0, G_RHO, s0.nd, P_zetab, P_zetac, P_zetaf);
     double Zp = Zold;
     if (Zp < P_depth) { Zp = P_depth + (double)kF32_1em3; if (P.TrackCollisions) D.hitB[n] += 1; }   // :900-903
     double P_zb = Zp, P_zc = Zp, P_zf = Zp;
@@ -405,7 +405,7 @@ LT_DEV void advect_particle(const LtDev& D, int n)
     for (int stg = 0; stg < 4; ++stg) {
         double Uad, Vad, Wad;
         stage_weights2(st, xs, ys);
-        find_currents2<T>(D, st, col, zs, P_zb, P_zc, P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad);
+        find_currents2<T, PH>(D, st, col, zs, P_zb, P_zc, P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad);
         double wgt = (stg == 0 || stg == 3) ? 1.0 : 2.0;
         sU += wgt * Uad; sV += wgt * Vad; sW += wgt * Wad;
         if (stg < 3) {
@@ -427,7 +427,7 @@ LT_DEV void advect_particle(const LtDev& D, int n)
         int deplvl = level_window2<false>(D, col, Zpar, P.us);
         const T* f2[2] = {(const T*)D.salt, (const T*)D.temp}; const Stencil* s2[2] = {&st.r, &st.r}; const int g2[2] = {G_RHO, G_RHO};
         double o[2];
-        wcts2<T, false, 2>(D, f2, s2, g2, st.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o);
+        wcts2<T, PH, false, 2>(D, f2, s2, g2, st.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o);
         D.psalt[n] = o[0]; D.ptemp[n] = o[1];
     }
     if (P.HTurbOn) {                                                     // hor_turb_module.f90:29-50
@@ -456,7 +456,6 @@ LT_DEV void advect_particle(const LtDev& D, int n)
 // window spans ~ +-15 knots = +-18% of the water column, the RDM step is ~1%).
 #define VW 32                      // knots held per window
 
-template <class T>
 struct VtCtx {
     const LtDev& D;
     int ws, p2;
@@ -469,7 +468,7 @@ struct VtCtx {
     bool sigerr;
     LT_DEV VtCtx(const LtDev& D_) : D(D_) {}
 
-    LT_DEV double knot_x(int k) const { return k <= 1 ? Z1 : (k >= p2 ? ZN : Z1 + ((double)k - 0.5) * H); }
+    LT_DEV double knot_x(int k) const { double x = fma((double)k - 0.5, H, Z1); x = k <= 1 ? Z1 : x; return k >= p2 ? ZN : x; }
     LT_DEV double newx(int t, int j) const { return zl[t][0] + (double)(j - 4) * hs[t]; }
     // piecewise-linear KH profile at newx(j): smallest jlo >= 1 with wz(jlo+1) > x (:135-166), pads (:169-177)
     LT_DEV double newy(int t, int j, int& lev) const
@@ -552,7 +551,7 @@ struct VtCtx {
     LT_DEV void need(int I) { if (I < ia || I > ib) build(max(1, min(I - VW / 2 + 1, p2 - VW + 1))); }
 };
 
-template <class T>
+template <class T, int PH>
 LT_DEV void vturb_particle(const LtDev& D, int n)
 {
     if (!D.s_act[n]) return;
@@ -563,12 +562,12 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights(s0.q, Xpar, Ypar, true);      // getInterp uses setInterp's weights
     ColK col; col.zb = D.s_zeb[n]; col.zc = D.s_zec[n]; col.zf = D.s_zef[n]; col.depth = D.s_depth[n]; col.h = -1.0 * col.depth;
     const double P_zc = D.s_pzc[n], P_depth = col.depth, P_zetac = col.zc;
-    VtCtx<T> V(D);
+    VtCtx V(D);
     V.ws = D.P.ws; V.p2 = 4 * V.ws; V.sigerr = false;
     const T* fk = (const T*)D.kh;
 #pragma unroll 1
     for (int l = 0; l < V.ws; ++l) {
-        gather_bcf<T>(D, fk, V.ws, l, s0, G_RHO, s0.nd, V.khp[0][l], V.khp[1][l], V.khp[2][l]);
+        gather_bcf<T, PH>(D, fk, V.ws, l, s0, G_RHO, s0.nd, V.khp[0][l], V.khp[1][l], V.khp[2][l]);
         zlev3<true>(D, col, l, V.zl[0][l], V.zl[1][l], V.zl[2][l]);
     }
     const double rp2 = 1.0 / (double)V.p2;
@@ -588,9 +587,9 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
         double Kprimec = 0.0;
         if (!(ParZc < P_depth || ParZc > P_zetac)) {
             int I = V.interval(ParZc); V.need(I);
-            int q = I - V.ka;
-            if (!V.sigerr) Kprimec = hpval_interval(ParZc, V.knot_x(I), V.knot_x(I + 1), V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
-            else Kprimec = qdiv(V.fy[q] - V.fy[q + 1], V.knot_x(I) - V.knot_x(I + 1));       // linint slope
+            int q = I - V.ka; const double X1 = V.knot_x(I), X2 = V.knot_x(I + 1);
+            if (!V.sigerr) Kprimec = hpval_interval(ParZc, X1, X2, V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
+            else Kprimec = qdiv(V.fy[q] - V.fy[q + 1], X1 - X2);       // linint slope
         }
         const double KprimeZc = -1.0 * Kprimec * deltat;
         const double Z3rdc = ParZc + 0.5 * KprimeZc;
@@ -598,9 +597,9 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
         if (Z3rdc < P_depth || Z3rdc > P_zetac) KH3rdc = background;
         else {
             int I = V.interval(Z3rdc); V.need(I);
-            int q = I - V.ka;
-            if (!V.sigerr) KH3rdc = hval_interval(Z3rdc, V.knot_x(I), V.knot_x(I + 1), V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
-            else { double m = qdiv(V.fy[q] - V.fy[q + 1], V.knot_x(I) - V.knot_x(I + 1)); KH3rdc = m * Z3rdc + (V.fy[q] - m * V.knot_x(I)); }
+            int q = I - V.ka; const double X1 = V.knot_x(I), X2 = V.knot_x(I + 1);
+            if (!V.sigerr) KH3rdc = hval_interval(Z3rdc, X1, X2, V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
+            else { double m = qdiv(V.fy[q] - V.fy[q + 1], X1 - X2); KH3rdc = m * Z3rdc + (V.fy[q] - m * X1); }
             if (KH3rdc < background) KH3rdc = background;
         }
         if ((i & 1) == 0) rnd = philox(g, 1u + (unsigned)(i >> 1));
@@ -734,7 +733,7 @@ LT_DEV int inpoly_banded(double x, double y, const double2* __restrict__ poly, d
     return crossed & 1;
 }
 
-template <class T>
+template <class T, int PH>
 LT_DEV void finish_particle(const LtDev& D, int n)
 {
     if (!D.s_act[n]) return;
@@ -751,7 +750,7 @@ LT_DEV void finish_particle(const LtDev& D, int n)
         st.u.nd = __ldg(D.U.node + (ue - 1));
         st.r.xp = Xpar; st.r.yp = Ypar; st.r.w = make_weights(st.r.q, Xpar, Ypar, false);
         col.zb = D.s_zeb[n]; col.zc = P_zetac; col.zf = D.s_zef[n]; col.depth = P_depth; col.h = -1.0 * P_depth;
-        bo = behave<T>(D, n, st, col, make_rng(D, n), Zpar, D.s_pzb[n], D.s_pzc[n], D.s_pzf[n], P_zetac, age, P_depth,
+        bo = behave<T, PH>(D, n, st, col, make_rng(D, n), Zpar, D.s_pzb[n], D.s_pzc[n], D.s_pzf[n], P_zetac, age, P_depth,
                        D.s_pu[n], D.s_pv[n], D.s_angle[n]);
     }
     double newXpos = D.s_nx[n], newYpos = D.s_ny[n];

@@ -16,23 +16,23 @@
 #include "lt_step2.cuh"
 
 // ------------------------------------------------------------------ kernels --
-template <class T>
-__global__ void __launch_bounds__(128) k_advect(const __grid_constant__ LtDev D)
+template <class T, int PH>
+__global__ void __launch_bounds__(128, 3) k_advect(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < D.n) advect_particle<T>(D, n);
+    if (n < D.n) advect_particle<T, PH>(D, n);
 }
-template <class T>
+template <class T, int PH>
 __global__ void __launch_bounds__(128) k_vturb(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < D.n) vturb_particle<T>(D, n);
+    if (n < D.n) vturb_particle<T, PH>(D, n);
 }
-template <class T>
+template <class T, int PH>
 __global__ void __launch_bounds__(128) k_finish(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < D.n) finish_particle<T>(D, n);
+    if (n < D.n) finish_particle<T, PH>(D, n);
 }
 
 // one ROMS record [level][node] (+ mask multiply, hydro:1371-1403) -> ring slot of the
@@ -609,16 +609,14 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
     }
     {
         int blocks = (D.n + 127) / 128;
-        if (ctx->esz == 4) {
-            k_advect<float><<<blocks, 128, 0, ctx->compute>>>(D);
-            if (ctx->prm.VTurbOn) k_vturb<float><<<blocks, 128, 0, ctx->compute>>>(D);
-            k_finish<float><<<blocks, 128, 0, ctx->compute>>>(D);
-        } else {
-            k_advect<double><<<blocks, 128, 0, ctx->compute>>>(D);
-            if (ctx->prm.VTurbOn) k_vturb<double><<<blocks, 128, 0, ctx->compute>>>(D);
-            k_finish<double><<<blocks, 128, 0, ctx->compute>>>(D);
-        }
-        ctx->launches += ctx->prm.VTurbOn ? 3 : 2;
+        const bool vt = ctx->prm.VTurbOn != 0;
+        cudaStream_t st = ctx->compute;
+#define LT_LAUNCH(T, PH) do { k_advect<T, PH><<<blocks, 128, 0, st>>>(D); if (vt) k_vturb<T, PH><<<blocks, 128, 0, st>>>(D); \
+                              k_finish<T, PH><<<blocks, 128, 0, st>>>(D); } while (0)
+#define LT_LAUNCH_T(T) do { switch (D.sb) { case 0: LT_LAUNCH(T, 0); break; case 1: LT_LAUNCH(T, 1); break; \
+                                            case 2: LT_LAUNCH(T, 2); break; default: LT_LAUNCH(T, 3); break; } } while (0)
+        if (ctx->esz == 4) LT_LAUNCH_T(float); else LT_LAUNCH_T(double);
+        ctx->launches += vt ? 3 : 2;
     }
     CK(cudaGetLastError());
     ctx->last_ix3 = D.ix[2];
