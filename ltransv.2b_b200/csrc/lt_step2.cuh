@@ -190,7 +190,7 @@ LT_DEV void stage_weights2(Stage2& s, double xp, double yp)
 }
 LT_DEV Rng make_rng(const LtDev& D, int n)
 {
-    long long gid = D.first_id + n;
+    long long gid = D.first_id + D.pid[n];
     Rng g; g.id_lo = (unsigned)((unsigned long long)gid & 0xffffffffull); g.id_hi = (unsigned)((unsigned long long)gid >> 32);
     g.step = D.gstep; g.seed = (unsigned)D.P.seed;
     return g;
@@ -334,7 +334,7 @@ LT_DEVN BehavOut behave(const LtDev& D, int n, const Stage2& s0, const ColK& col
 LT_DEV void particle_error(const LtDev& D, int n, int code, double revertZ)
 {
     int EF = D.P.ErrorFlag;
-    int gid = (int)(D.first_id + n);
+    int gid = (int)(D.first_id + D.pid[n]);
     if (EF < 1 || EF > 3) atomicMin(D.bad, gid);                         // STOP: lowest id wins
     else if (EF == 1) D.z[n] = revertZ;                                  // pn = p (x, y unchanged)
     else if (EF == 2) D.flags[n] |= LT_F_DEAD;
@@ -606,7 +606,7 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
         const double DEV = (i & 1) ? box_muller(D, rnd.z, rnd.w) : box_muller(D, rnd.x, rnd.y);
         ParZc = ParZc + KprimeZc + DEV * sqrt(2.0 * KH3rdc * deltat);  // (...)**0.5, ledger 12
 #ifdef LT_DEBUG_TRACE
-        if (D.first_id + n == D.dbg_id) { D.dbg[4 * i] = ParZc; D.dbg[4 * i + 1] = Kprimec; D.dbg[4 * i + 2] = KH3rdc; D.dbg[4 * i + 3] = DEV; }
+        if (D.first_id + D.pid[n] == D.dbg_id) { D.dbg[4 * i] = ParZc; D.dbg[4 * i + 1] = Kprimec; D.dbg[4 * i + 2] = KH3rdc; D.dbg[4 * i + 3] = DEV; }
 #endif
     }
     D.s_turbv[n] = P_zc - ParZc;                                        // :342

@@ -48,6 +48,7 @@ struct LtDev {
     uint8_t* flags;             // bit0 settled, bit1 dead, bit2 oob, bit3 bottom (behaviour 7)
     int8_t* behave;             // P_behave
     int n; long long first_id;
+    const int* pid;             // slot -> local particle index (particles are periodically re-sorted by cell)
     // events
     ltgpu_event* ev; int* nev; int evcap; int* bad;
     // per-particle scratch passed between the three step kernels (SoA)

@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include "lt_step2.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 // ------------------------------------------------------------------ kernels --
 template <class T, int PH>
@@ -53,6 +54,42 @@ __global__ void k_fill_slot(const TI* __restrict__ in, const uint8_t* __restrict
         int n = n0 + nn, k = k0 + threadIdx.x;
         if (n < nodes && k < L) out[((size_t)n * L + k) * 4 + slot] = (TO)tile[threadIdx.x][nn];
     }
+}
+
+// ---- periodic re-sort of the particle slots by (rho element, depth bin) -------------------
+// Particles never interact, so slot order is free.  Keeping the lanes of a warp in the same
+// cell and the same part of the water column makes their stencil gathers hit the same
+// sectors and -- more important for this FP64 code -- makes them take the same branches
+// (spline interval, tension regime, Newton iteration counts, boundary tests).
+__global__ void k_sort_keys(const LtDev D, unsigned* __restrict__ key, int* __restrict__ idx)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= D.n) return;
+    int re = D.r_ele[n];
+    int4 nd = __ldg(D.R.node + (max(re, 1) - 1));
+    double h = 0.25 * (__ldg(D.depth + nd.x) + __ldg(D.depth + nd.y) + __ldg(D.depth + nd.z) + __ldg(D.depth + nd.w));
+    int bin = (int)(-8.0 * D.z[n] / fmax(h, 1e-3));
+    bin = max(0, min(7, bin));
+    bool idle = (D.flags[n] & (LT_F_SETTLED | LT_F_DEAD | LT_F_OOB)) != 0;
+    key[n] = idle ? 0xffffffffu : ((unsigned)re << 3) | (unsigned)bin;      // inactive particles go last
+    idx[n] = n;
+}
+template <class V>
+__global__ void k_gather(const V* __restrict__ in, V* __restrict__ out, const int* __restrict__ perm, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+template <class V>
+__global__ void k_scatter(const V* __restrict__ in, V* __restrict__ out, const int* __restrict__ pid, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[pid[i]] = in[i];
+}
+__global__ void k_iota(int* p, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
 }
 
 __global__ void k_status(const LtDev D, int* __restrict__ status)
@@ -131,6 +168,13 @@ struct ltgpu_ctx {
     std::string err;
     bool have_grid = false, have_bounds = false, have_particles = false, have_habitat = false;
     int nthreads_grid = 0;
+    // re-sort state
+    bool sort_on = true;
+    unsigned *d_key = nullptr, *d_key2 = nullptr; int *d_idx = nullptr, *d_perm = nullptr, *d_pid = nullptr;
+    void* d_cub = nullptr; size_t cub_bytes = 0;
+    double* spare8 = nullptr; int* spare4 = nullptr; uint8_t* spare1 = nullptr; double* out8 = nullptr;
+    int key_bits = 32;
+    long long sorts = 0;
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -277,6 +321,46 @@ static int32_t build_indices(ltgpu_ctx* ctx, const std::vector<double4>& seg, co
     return LTGPU_OK;
 }
 
+// ---------------------------------------------------------------- re-sort ----
+template <class V>
+static void permute(ltgpu_ctx* ctx, V** arr, V** spare)
+{
+    int n = ctx->D.n;
+    k_gather<V><<<(n + 255) / 256, 256, 0, ctx->compute>>>(*arr, *spare, ctx->d_perm, n);
+    std::swap(*arr, *spare);
+    ctx->launches++;
+}
+static int32_t resort(ltgpu_ctx* ctx)
+{
+    LtDev& D = ctx->D; int n = D.n;
+    k_sort_keys<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_key, ctx->d_idx);
+    CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_perm, n, 0, ctx->key_bits, ctx->compute));
+    ctx->launches += 2;
+    double** a8[] = {&D.x, &D.y, &D.z, &D.age, &D.dob, &D.lifespan, &D.psalt, &D.ptemp, &D.timer, &D.sprev, &D.zprev};
+    for (auto p : a8) permute(ctx, p, &ctx->spare8);
+    int** a4[] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly, &ctx->d_pid};
+    for (auto p : a4) permute(ctx, p, &ctx->spare4);
+    permute(ctx, &D.flags, &ctx->spare1);
+    { uint8_t* b = (uint8_t*)D.behave; permute(ctx, &b, &ctx->spare1); D.behave = (int8_t*)b; }
+    D.pid = ctx->d_pid;
+    CK(cudaGetLastError());
+    ctx->sorts++;
+    return LTGPU_OK;
+}
+// copy one per-slot column to the host in particle order
+template <class V>
+static int32_t fetch_col(ltgpu_ctx* ctx, V* host, const V* dev)
+{
+    if (!host) return LTGPU_OK;
+    int n = ctx->D.n;
+    V* tmp = (V*)ctx->out8;
+    k_scatter<V><<<(n + 255) / 256, 256, 0, ctx->compute>>>(dev, tmp, ctx->d_pid, n);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(host, tmp, sizeof(V) * (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    return LTGPU_OK;
+}
+
 extern "C" {
 
 int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
@@ -307,6 +391,8 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming);
     cudaEventCreate(&ctx->t0); cudaEventCreate(&ctx->t1);
     ctx->D.sb = 0; ctx->D.sc = 1; ctx->D.sf = 2; ctx->spare = 3;
+    const char* so = getenv("LTGPU_SORT");
+    ctx->sort_on = !(so && so[0] == '0');
     *out = ctx;
     return LTGPU_OK;
 }
@@ -516,6 +602,18 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
                      &D.s_nx, &D.s_ny, &D.s_advz, &D.s_pu, &D.s_pv, &D.s_turbv};
     for (auto p : sc) TRY(dalloc(ctx, p, N));
     TRY(dalloc(ctx, &D.s_act, N));
+    TRY(dalloc(ctx, &ctx->d_pid, N)); TRY(dalloc(ctx, &ctx->d_perm, N)); TRY(dalloc(ctx, &ctx->d_idx, N));
+    TRY(dalloc(ctx, &ctx->d_key, N)); TRY(dalloc(ctx, &ctx->d_key2, N));
+    TRY(dalloc(ctx, &ctx->spare8, N)); TRY(dalloc(ctx, &ctx->spare4, N)); TRY(dalloc(ctx, &ctx->spare1, N)); TRY(dalloc(ctx, &ctx->out8, N));
+    k_iota<<<(n + 255) / 256, 256, 0, ctx->compute>>>(ctx->d_pid, n);
+    D.pid = ctx->d_pid;
+    {
+        int bits = 3; while ((1ll << bits) < ((long long)(D.R.nE + 1) << 3)) ++bits;
+        ctx->key_bits = 32;                               // idle particles use key 0xffffffff
+        (void)bits;
+        cub::DeviceRadixSort::SortPairs(nullptr, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_perm, n, 0, ctx->key_bits, ctx->compute);
+        void* q = nullptr; CK(cudaMalloc(&q, std::max<size_t>(ctx->cub_bytes, 16))); ctx->owned.push_back(q); ctx->d_cub = q;
+    }
     CK(cudaStreamSynchronize(ctx->compute));
     ctx->have_particles = true;
     return LTGPU_OK;
@@ -587,6 +685,7 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
     CK(cudaSetDevice(ctx->device));
     LtDev& D = ctx->D;
     const int dt = ctx->prm.dt, idt = ctx->prm.idt;
+    if (ctx->sort_on && it == 1) TRY(resort(ctx));
     D.p = p; D.it = it;
     D.ex[0] = (double)((p - 2) * dt); D.ex[1] = (double)((p - 1) * dt); D.ex[2] = (double)(p * dt);   // LTRANS.f90:568-571
     D.ix[0] = D.ex[1] + (double)((it - 2) * idt);                                                      // :588-590
@@ -653,13 +752,13 @@ int32_t ltgpu_fetch(ltgpu_ctx* ctx, double* x, double* y, double* z, double* age
     CK(cudaSetDevice(ctx->device));
     LtDev& D = ctx->D; size_t N = D.n; cudaStream_t s = ctx->compute;
     if (status) { k_status<<<(D.n + 255) / 256, 256, 0, s>>>(D, ctx->d_status); ctx->launches++; }
-    struct { void* h; const void* d; size_t b; } c[] = {
-        {x, D.x, N * 8}, {y, D.y, N * 8}, {z, D.z, N * 8}, {age, D.age, N * 8}, {status, ctx->d_status, N * 4},
-        {salt, D.psalt, N * 8}, {temp, D.ptemp, N * 8}, {hitBottom, D.hitB, N * 4}, {hitLand, D.hitL, N * 4},
-        {endpoly, D.endpoly, N * 4}, {lifespan, D.lifespan, N * 8}, {r_ele, D.r_ele, N * 4}, {u_ele, D.u_ele, N * 4},
-        {v_ele, D.v_ele, N * 4}};
-    for (auto& q : c) if (q.h) CK(cudaMemcpyAsync(q.h, q.d, q.b, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    TRY(fetch_col(ctx, x, (const double*)D.x)); TRY(fetch_col(ctx, y, (const double*)D.y)); TRY(fetch_col(ctx, z, (const double*)D.z));
+    TRY(fetch_col(ctx, age, (const double*)D.age)); TRY(fetch_col(ctx, status, (const int*)ctx->d_status));
+    TRY(fetch_col(ctx, salt, (const double*)D.psalt)); TRY(fetch_col(ctx, temp, (const double*)D.ptemp));
+    TRY(fetch_col(ctx, hitBottom, (const int*)D.hitB)); TRY(fetch_col(ctx, hitLand, (const int*)D.hitL));
+    TRY(fetch_col(ctx, endpoly, (const int*)D.endpoly)); TRY(fetch_col(ctx, lifespan, (const double*)D.lifespan));
+    TRY(fetch_col(ctx, r_ele, (const int*)D.r_ele)); TRY(fetch_col(ctx, u_ele, (const int*)D.u_ele)); TRY(fetch_col(ctx, v_ele, (const int*)D.v_ele));
+    (void)N; (void)s;
     return LTGPU_OK;
 }
 
@@ -722,12 +821,17 @@ int32_t ltgpu_device_ptr(ltgpu_ctx* ctx, int32_t which, void** dptr)
     if (!ctx || !dptr) return LTGPU_E_ARG;
     ARG(ctx->have_particles, "device_ptr before set_particles");
     LtDev& D = ctx->D;
-    switch (which) {
-    case 0: *dptr = D.x; break; case 1: *dptr = D.y; break; case 2: *dptr = D.z; break;
-    case 3: *dptr = D.age; break;
-    case 4: k_status<<<(D.n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_status); ctx->launches++; *dptr = ctx->d_status; break;
-    default: ctx->err = "device_ptr: which out of range"; return LTGPU_E_ARG;
-    }
+    // slots are re-sorted by cell; hand out a particle-order copy (valid until the next call)
+    int n = D.n;
+    if (which >= 0 && which <= 3) {
+        const double* src = which == 0 ? D.x : which == 1 ? D.y : which == 2 ? D.z : D.age;
+        k_scatter<double><<<(n + 255) / 256, 256, 0, ctx->compute>>>(src, ctx->out8, ctx->d_pid, n);
+        ctx->launches++; *dptr = ctx->out8;
+    } else if (which == 4) {
+        k_status<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_status);
+        k_scatter<int><<<(n + 255) / 256, 256, 0, ctx->compute>>>(ctx->d_status, (int*)ctx->out8, ctx->d_pid, n);
+        ctx->launches += 2; *dptr = ctx->out8;
+    } else { ctx->err = "device_ptr: which out of range"; return LTGPU_E_ARG; }
     return LTGPU_OK;
 }
 
