@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+TRAFFIC_BYTES_PER_STEP = None   # dram bytes of the 3 kernels per internal step per 1e6 particles (ncu, profiles/)
 B_ALG = 3624          # algorithmic bytes / particle-step, config 2
 NPART = 1_000_000
 WORKLOAD = "baymouth-shape 130x130x20 synthetic ROMS, 1M particles/GPU, HTurb+VTurb, 30 internal steps per step"
@@ -209,6 +210,11 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e.item())
     stop.set(); th.join()
+    # ---- per-kernel device times (separate short pass: the bracketing syncs every step) -----
+    g.kernel_times(True)
+    one_step(False)
+    kms, ksteps = g.kernel_times(False)
+    k_adv, k_vt, k_fin = (v / max(1, ksteps) for v in kms[:3])
     # settlement / statistics reduction over NVLink (north star: the only collective)
     stats_t.copy_(torch.from_numpy(g.stats()))
     if world_size > 1:
@@ -216,7 +222,8 @@ def main():
     total_steps = n * world_size * stepIT * args.steps
     value = total_steps / (dev_ms * 1e-3)
     e2e = total_steps / e2e_s
-    kern_ms = dev_ms / (args.steps * stepIT)                  # one k_step launch over n particles
+    kern_ms = k_adv + k_vt + k_fin                            # the three launches of one internal step
+    step_ms = dev_ms / (args.steps * stepIT)                  # same, from the timed region (incl. re-sort, refill waits)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -236,9 +243,14 @@ def main():
             "e2e": {"value": e2e, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_step<float>", "kernel_ms": kern_ms,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "note": "algorithmic bytes 3624 B/particle-step x particles per launch / mean launch time"},
+                         "traffic": TRAFFIC_BYTES_PER_STEP * (n / 1e6) if TRAFFIC_BYTES_PER_STEP else None,
+                         "kernel": "k_advect + k_vturb + k_finish (the three launches of one internal step; k_vturb dominates)",
+                         "kernel_ms": kern_ms, "kernels_ms": {"k_advect": k_adv, "k_vturb": k_vt, "k_finish": k_fin},
+                         "internal_step_ms_in_timed_region": step_ms,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650",
+                         "note": "achieved = 3624 algorithmic B/particle-step x particles per launch / summed launch time; "
+                                 "the path is FP64-latency bound, not HBM bound (DESIGN.md section 5): fields are L2-resident, "
+                                 "dram traffic is particle state + per-thread spline scratch"},
             "clocks": clocks_summary(samples),
             "stats": {"settled": int(stats_t[0]), "dead": int(stats_t[1]), "out_of_bounds": int(stats_t[2]),
                       "active": int(stats_t[6]), "events": int(stats_t[5])},

@@ -209,6 +209,10 @@ int32_t ltgpu_device_ptr(ltgpu_ctx* ctx, int32_t which, void** dptr);
  * (torch.cuda.Event only sees torch's current stream). */
 int32_t ltgpu_timer_start(ltgpu_ctx* ctx);
 int32_t ltgpu_timer_stop(ltgpu_ctx* ctx, float* ms);
+/* Per-kernel device times of the step (k_advect, k_vturb, k_finish, reserved), summed over
+ * the internal steps since the last call; enable != 0 switches the CUDA-event bracketing on
+ * (it synchronises every step, so it is a measurement mode, not for production runs). */
+int32_t ltgpu_kernel_times(ltgpu_ctx* ctx, int32_t enable, float ms[4], int64_t* steps);
 /* number of kernels this context has launched so far */
 int64_t ltgpu_launch_count(const ltgpu_ctx* ctx);
 /* raw cudaStream_t of the compute stream */

@@ -17,20 +17,29 @@
 #include <cub/device/device_radix_sort.cuh>
 
 // ------------------------------------------------------------------ kernels --
+#ifndef LT_LB_ADV
+#define LT_LB_ADV 4
+#endif
+#ifndef LT_LB_VT
+#define LT_LB_VT 6
+#endif
+#ifndef LT_LB_FIN
+#define LT_LB_FIN 4
+#endif
 template <class T, int PH>
-__global__ void __launch_bounds__(128, 3) k_advect(const __grid_constant__ LtDev D)
+__global__ void __launch_bounds__(128, LT_LB_ADV) k_advect(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < D.n) advect_particle<T, PH>(D, n);
 }
 template <class T, int PH>
-__global__ void __launch_bounds__(128) k_vturb(const __grid_constant__ LtDev D)
+__global__ void __launch_bounds__(128, LT_LB_VT) k_vturb(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < D.n) vturb_particle<T, PH>(D, n);
 }
 template <class T, int PH>
-__global__ void __launch_bounds__(128) k_finish(const __grid_constant__ LtDev D)
+__global__ void __launch_bounds__(128, LT_LB_FIN) k_finish(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < D.n) finish_particle<T, PH>(D, n);
@@ -175,6 +184,8 @@ struct ltgpu_ctx {
     double* spare8 = nullptr; int* spare4 = nullptr; uint8_t* spare1 = nullptr; double* out8 = nullptr;
     int key_bits = 32;
     long long sorts = 0;
+    // optional per-kernel timing (ltgpu_kernel_times)
+    bool timing = false; cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; float tacc[4] = {0, 0, 0, 0}; long long tcount = 0;
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -408,6 +419,7 @@ int32_t ltgpu_destroy(ltgpu_ctx* ctx)
     if (ctx->slot_free) cudaEventDestroy(ctx->slot_free);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
+    for (int k = 0; k < 5; ++k) if (ctx->tev[k]) cudaEventDestroy(ctx->tev[k]);
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     delete ctx;
@@ -710,12 +722,19 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
         int blocks = (D.n + 127) / 128;
         const bool vt = ctx->prm.VTurbOn != 0;
         cudaStream_t st = ctx->compute;
-#define LT_LAUNCH(T, PH) do { k_advect<T, PH><<<blocks, 128, 0, st>>>(D); if (vt) k_vturb<T, PH><<<blocks, 128, 0, st>>>(D); \
-                              k_finish<T, PH><<<blocks, 128, 0, st>>>(D); } while (0)
+#define LT_LAUNCH(T, PH) do { if (ctx->timing) cudaEventRecord(ctx->tev[0], st); \
+                              k_advect<T, PH><<<blocks, 128, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[1], st); \
+                              if (vt) k_vturb<T, PH><<<blocks, 128, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[2], st); \
+                              k_finish<T, PH><<<blocks, 128, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[3], st); } while (0)
 #define LT_LAUNCH_T(T) do { switch (D.sb) { case 0: LT_LAUNCH(T, 0); break; case 1: LT_LAUNCH(T, 1); break; \
                                             case 2: LT_LAUNCH(T, 2); break; default: LT_LAUNCH(T, 3); break; } } while (0)
         if (ctx->esz == 4) LT_LAUNCH_T(float); else LT_LAUNCH_T(double);
         ctx->launches += vt ? 3 : 2;
+        if (ctx->timing) {
+            cudaEventSynchronize(ctx->tev[3]);
+            for (int k = 0; k < 3; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ctx->tev[k], ctx->tev[k + 1]); ctx->tacc[k] += ms; }
+            ctx->tcount++;
+        }
     }
     CK(cudaGetLastError());
     ctx->last_ix3 = D.ix[2];
@@ -861,6 +880,17 @@ int32_t ltgpu_debug_trace(ltgpu_ctx* ctx, int64_t id, double* out, int32_t n)
     return 0;
 }
 #endif
+int32_t ltgpu_kernel_times(ltgpu_ctx* ctx, int32_t enable, float ms[4], int64_t* steps)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ms) { for (int k = 0; k < 4; ++k) ms[k] = ctx->tacc[k]; }
+    if (steps) *steps = ctx->tcount;
+    for (int k = 0; k < 4; ++k) ctx->tacc[k] = 0; ctx->tcount = 0;
+    if (enable && !ctx->tev[0]) for (int k = 0; k < 5; ++k) CK(cudaEventCreate(&ctx->tev[k]));
+    ctx->timing = enable != 0;
+    return LTGPU_OK;
+}
 int64_t ltgpu_launch_count(const ltgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* ltgpu_stream(ltgpu_ctx* ctx) { return ctx ? (void*)ctx->compute : nullptr; }
 

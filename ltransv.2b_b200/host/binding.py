@@ -19,7 +19,7 @@ LTGPU_F32, LTGPU_F64 = 4, 8
 LTGPU_RNG_PHILOX = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(os.path.dirname(_HERE), "csrc", "libltrans_b200.so")
+DEFAULT_LIB = os.environ.get("LTRANS_B200_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libltrans_b200.so")
 
 
 class LtransError(RuntimeError):
@@ -256,6 +256,12 @@ class LtransLib:
         ms = C.c_float(0)
         self._check(self._fn("timer_stop")(self.ctx, C.byref(ms)), "timer_stop")
         return ms.value
+
+    def kernel_times(self, enable=True):
+        ms = (C.c_float * 4)()
+        steps = C.c_int64(0)
+        self._check(self._fn("kernel_times")(self.ctx, C.c_int32(1 if enable else 0), ms, C.byref(steps)), "kernel_times")
+        return [float(v) for v in ms], int(steps.value)
 
     def launch_count(self):
         return int(self._fn("launch_count")(self.ctx))
