@@ -40,6 +40,30 @@ LT_DEV double qdiv(double a, double b)
 #endif
 }
 
+// exp(x) for x in [-746, 0] (every use in TSPACK is exp(-sigma), exp(-sigma b)): Cody-Waite
+// reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation
+// 0.347^14/14! = 4e-18 < 2^-53), scaling by 2^k through the exponent field.  < 1 ulp; about
+// half the instructions of the general-purpose exp() (no overflow / NaN / positive paths).
+LT_DEV double exp_neg(double x)
+{
+#ifdef LT_IEEE_DIV
+    return exp(x);
+#else
+    if (x < -708.0) return 0.0;
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);     // round to nearest via the magic constant
+    const int k = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                                    // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);  p = fma(p, r, 2.505210838544172e-08); p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06); p = fma(p, r, 2.48015873015873e-05); p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.3888888888888889e-03); p = fma(p, r, 8.333333333333333e-03); p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01); p = fma(p, r, 0.5); p = fma(p, r, 1.0); p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));   // k >= -1022 here: no denormals
+#endif
+}
+
 #define kF32_1em3 0.001f        // DBLE(0.001)    is a float32 literal widened (LTRANS.f90:901)
 #define kF32_1em6 0.000001f     // DBLE(0.000001) likewise                     (LTRANS.f90:1002)
 
@@ -281,67 +305,79 @@ LT_DEV void snhcsh(double X, double& SINHM, double& COSHM, double& COSHMM)
 // SIGMA zeroed on entry), so solving only the interval that is evaluated gives the
 // value the reference's full sweep stores for it.  err = 1 <=> NIT > 10000 (SigErr).
 #define LT_RTOL (200.0 * 1.1102230246251565e-16)      /* 200 * 2^-53, the :433-439 loop */
-LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double S2, int& err)
+// One Newton iteration of the convexity equation  SIG * T1(SIG) = TP1  (tension:528-579).
+// Returns true when the loop of the reference would exit; `out` is then the tension factor
+// (0 with err = 1 when the reference would raise SigErr).  State: SIG, NIT, chk, chk_at.
+struct NewtonState { double SIG, TP1, chk; int NIT, chk_at; };
+LT_DEV void newton_start(NewtonState& q, double TP1, double SIG0) { q.SIG = SIG0; q.TP1 = TP1; q.chk = SIG0; q.NIT = 0; q.chk_at = 1; }
+LT_DEV bool newton_step(NewtonState& q, double& out, int& err)
+{
+    const double SBIG = 85.0, RTOL = LT_RTOL, FTOL = 0.0;
+    double T1, FP, SIG = q.SIG;
+    if (SIG <= .5) {
+        double SINHM, COSHM, COSHMM;
+        snhcsh(SIG, SINHM, COSHM, COSHMM);
+        double RS_ = qrcp(SINHM);
+        T1 = COSHM * RS_;
+        FP = T1 + SIG * (SIG * RS_ - T1 * T1 + 1.0);
+    } else {
+        double EMS = exp_neg(-SIG);
+        double SSM = 1.0 - EMS * (EMS + SIG + SIG);
+        double RM_ = qrcp(SSM);
+        T1 = (1.0 - EMS) * (1.0 - EMS) * RM_;
+        FP = T1 + SIG * (2.0 * SIG * EMS * RM_ - T1 * T1 + 1.0);
+    }
+    double F = SIG * T1 - q.TP1;
+    if (++q.NIT > 10000) { err = 1; out = 0.0; return true; }         // tension:556-559
+    if (FP <= 0.0) { out = fmin(SIG, SBIG); return true; }
+    double DSIG = -qdiv(F, FP);
+    if (fabs(DSIG) <= RTOL * SIG || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) { out = fmin(SIG, SBIG); return true; }
+    SIG = SIG + DSIG;
+    q.SIG = SIG;
+    // Newton's map SIG -> SIG' is a pure function of SIG.  When F's rounding noise sits just
+    // above RTOL the iteration falls into a short cycle and the reference spins until
+    // NIT > 10000 and raises SigErr.  A repeated iterate proves the cycle, so Brent's
+    // checkpointing reaches the same verdict without 10^4 iterations.
+    if (SIG == q.chk) { err = 1; out = 0.0; return true; }
+    if (q.NIT == q.chk_at) { q.chk = SIG; q.chk_at <<= 1; }
+    return false;
+}
+
+// SIGS classification of one interval (tension:314-527, 638-760).  Returns true when the
+// tension factor is known (`sigma`); false when the convexity Newton solve is needed
+// (TP1, SIG0 filled).  The monotonicity secant iteration (rare: data with an inflection
+// inside the interval) is solved here.
+LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2, double& sigma, double& TP1o, double& SIG0, int& err)
 {
     const double SBIG = 85.0, RTOL = LT_RTOL, FTOL = 0.0;
     double S = qdiv(Y2 - Y1, DX);
     double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
-    if ((D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0)) return SBIG;
+    if ((D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0)) { sigma = SBIG; return true; }
     double SIG = 0.0;
     if (D1D2 >= 0.0) {
-        if (D1D2 == 0.0) return 0.0;
+        if (D1D2 == 0.0) { sigma = 0.0; return true; }
         double T = fmax(qdiv(D1, D2), qdiv(D2, D1));
-        if (T <= 2.0) return 0.0;
-        double TP1 = T + 1.0;
-        SIG = sqrt(10.0 * T - 20.0);
-        int NIT = 0;
-        // Newton's map SIG -> SIG' is a pure function of SIG.  When F's rounding noise sits
-        // just above RTOL the iteration falls into a short cycle and the reference spins until
-        // NIT > 10000 and raises SigErr (tension:556-559).  A repeated iterate proves the
-        // cycle, so Brent's checkpointing reaches the same verdict without 10^4 iterations.
-        double chk = SIG; int chk_at = 1;
-        for (;;) {
-            double T1, FP;
-            if (SIG <= .5) {
-                double SINHM, COSHM, COSHMM;
-                snhcsh(SIG, SINHM, COSHM, COSHMM);
-                double RS_ = qrcp(SINHM);
-                T1 = COSHM * RS_;
-                FP = T1 + SIG * (SIG * RS_ - T1 * T1 + 1.0);
-            } else {
-                double EMS = exp(-SIG);
-                double SSM = 1.0 - EMS * (EMS + SIG + SIG);
-                double RM_ = qrcp(SSM);
-                T1 = (1.0 - EMS) * (1.0 - EMS) * RM_;
-                FP = T1 + SIG * (2.0 * SIG * EMS * RM_ - T1 * T1 + 1.0);
-            }
-            double F = SIG * T1 - TP1;
-            if (++NIT > 10000) { err = 1; return 0.0; }
-            if (FP <= 0.0) break;
-            double DSIG = -qdiv(F, FP);
-            if (fabs(DSIG) <= RTOL * SIG || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
-            SIG = SIG + DSIG;
-            if (SIG == chk) { err = 1; return 0.0; }
-            if (NIT == chk_at) { chk = SIG; chk_at <<= 1; }
-        }
-        return fmin(SIG, SBIG);
+        if (T <= 2.0) { sigma = 0.0; return true; }
+        TP1o = T + 1.0;
+        SIG0 = sqrt(10.0 * T - 20.0);
+        return false;
     }
     // monotonicity :638-760
-    if (S1 * S < 0.0 || S2 * S < 0.0) return 0.0;
+    if (S1 * S < 0.0 || S2 * S < 0.0) { sigma = 0.0; return true; }
     double T0 = 3.0 * S - S1 - S2;
     double D0 = T0 * T0 - S1 * S2;
-    if (D0 <= 0.0 || S * T0 >= 0.0) return 0.0;
+    if (D0 <= 0.0 || S * T0 >= 0.0) { sigma = 0.0; return true; }
     double SGN = copysign(1.0, S);
     SIG = SBIG;
     double FMAX = qdiv(SGN * (SIG * S - S1 - S2), SIG - 2.0);
-    if (FMAX <= 0.0) return SBIG;
+    if (FMAX <= 0.0) { sigma = SBIG; return true; }
     double STOL = RTOL * SIG, F = FMAX, F0 = qdiv(SGN * D0, 3.0 * (D1 - D2)), FNEG = F0;
     double DSIG = SIG, DMAX = SIG, D1PD2 = D1 + D2, A = 0.0, E = 0.0;
     bool CONT = true;                                  // ledger 18
     int NIT = 0;
     for (;;) {
         DSIG = qdiv(-F * DSIG, F - F0);
-        if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { err = 1; return 0.0; } continue; }
+        if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { err = 1; sigma = 0.0; return true; } continue; }
         if (fabs(DSIG) < STOL / 2.0) DSIG = -copysign(STOL / 2.0, DMAX);
         SIG = SIG + DSIG;
         F0 = F;
@@ -354,7 +390,7 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
             A = C2 - C1;
             E = SIG * SINHM - COSHMM - COSHMM;
         } else {
-            double EMS = exp(-SIG), EMS2 = EMS + EMS, TM = 1.0 - EMS;
+            double EMS = exp_neg(-SIG), EMS2 = EMS + EMS, TM = 1.0 - EMS;
             double SSINH = TM * (1.0 + EMS), SSM = SSINH - SIG * EMS2, SCM = TM * TM;
             C1 = SIG * SCM * D2 - SSM * D1PD2;
             C2 = SIG * SSINH * D2 - SCM * D1PD2;
@@ -366,7 +402,7 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
             if (CONT) E = SIG * SSINH - SCM - SCM;
         }
         if (CONT) F = qdiv(SGN * (E * S2 - C2) + sqrt(A * (C2 + C1)), E);
-        if (++NIT > 100000) { err = 1; return 0.0; }
+        if (++NIT > 100000) { err = 1; sigma = 0.0; return true; }
         STOL = RTOL * SIG;
         if (fabs(DMAX) <= STOL || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
         DMAX = DMAX + DSIG;
@@ -377,7 +413,21 @@ LT_DEVN double sigs_interval(double DX, double Y1, double Y2, double S1, double 
             if (fabs(DSIG) > fabs(T1) && fabs(F) < fabs(T2)) { DSIG = T1; F0 = T2; }
         }
     }
-    return fmin(SIG, SBIG);
+    sigma = fmin(SIG, SBIG);
+    return true;
+}
+
+
+// SIGS for one interval, solved on the spot (intervals are independent in SIGS: TOL = 0 and
+// SIGMA zeroed on entry, so solving only the interval that is evaluated gives the value the
+// reference's full sweep stores for it).  err = 1 <=> SigErr.
+LT_DEV double sigs_interval(double DX, double Y1, double Y2, double S1, double S2, int& err)
+{
+    double sigma, TP1, SIG0;
+    if (sigs_classify(DX, Y1, Y2, S1, S2, sigma, TP1, SIG0, err)) return sigma;
+    NewtonState q; newton_start(q, TP1, SIG0);
+    while (!newton_step(q, sigma, err)) {}
+    return sigma;
 }
 
 // HVAL on one interval (tension_module.f90:1043-1117)
@@ -395,7 +445,7 @@ LT_DEVN double hval_interval(double T, double X1, double X2, double Y1, double Y
     }
     double SB1 = SIG * B1, SB2 = SIG - SB1;
     if (-SB1 > SBIG || -SB2 > SBIG) return Y1 + S * U;
-    double E1 = exp(-SB1), E2 = exp(-SB2), EMS = E1 * E2, TM = 1.0 - EMS, TS = TM * TM, TP = 1.0 + EMS;
+    double E1 = exp_neg(-SB1), E2 = exp_neg(-SB2), EMS = E1 * E2, TM = 1.0 - EMS, TS = TM * TM, TP = 1.0 + EMS;
     double E = TM * (SIG * TP - TM - TM);
     return Y1 + S * U + DX * (TM * (TP - E1 - E2) * (D1 + D2) +
            SIG * ((E2 + EMS * (E1 - 2.0) - B1 * TS) * D1 + (E1 + EMS * (E2 - 2.0) - B2 * TS) * D2)) * qrcp(SIG * E);
@@ -415,7 +465,7 @@ LT_DEVN double hpval_interval(double T, double X1, double X2, double Y1, double 
     }
     double SB1 = SIG * B1, SB2 = SIG - SB1;
     if (-SB1 > SBIG || -SB2 > SBIG) return S;
-    double E1 = exp(-SB1), E2 = exp(-SB2), EMS = E1 * E2, TM = 1.0 - EMS;
+    double E1 = exp_neg(-SB1), E2 = exp_neg(-SB2), EMS = E1 * E2, TM = 1.0 - EMS;
     double E = TM * (SIG * (1.0 + EMS) - TM - TM);
     return S + (TM * ((E2 - E1) * (D1 + D2) + TM * (D1 - D2)) + SIG * ((E1 * EMS - E2) * D1 + (E1 - E2 * EMS) * D2)) * qrcp(E);
 }

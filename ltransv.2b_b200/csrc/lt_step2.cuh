@@ -78,20 +78,23 @@ LT_DEV void knots_prepare(Knots4& k)
     double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
     k.r1 = qrcp(d1); k.r2 = qrcp(d2); k.r3 = qrcp(d3); k.r12 = qrcp(d1 + d2); k.r23 = qrcp(d2 + d3);
 }
-LT_DEVN double spline4_eval2(const Knots4& k, double y0, double y1, double y2, double y3, double T)
+// the interval of a 4-knot spline that contains T, with its end slopes (YPC1) -- everything
+// SIGS and HVAL need (tension:852-978, 1026-1041)
+struct Iv4 { double X1, X2, Y1, Y2, P1, P2; };
+LT_DEV void spline4_prepare(const Knots4& k, double y0, double y1, double y2, double y3, double T, Iv4& v)
 {
-    double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
-    double s1 = (y1 - y0) * k.r1, s2 = (y2 - y1) * k.r2, s3 = (y3 - y2) * k.r3;
-    int I = (T < k.x[0]) ? 0 : (T > k.x[3]) ? 2 : (T < k.x[2] ? (T < k.x[1] ? 0 : 1) : 2);
-    double X1, X2, Y1, Y2, P1, P2;
-    double pm1 = ypc1_mid_r(d1, d2, s1, s2, k.r12), pm2 = ypc1_mid_r(d2, d3, s2, s3, k.r23);
-    if (I == 0) { X1 = k.x[0]; X2 = k.x[1]; Y1 = y0; Y2 = y1; P1 = ypc1_end(s1, s1 + d1 * (s1 - s2) * k.r12); P2 = pm1; }
-    else if (I == 1) { X1 = k.x[1]; X2 = k.x[2]; Y1 = y1; Y2 = y2; P1 = pm1; P2 = pm2; }
-    else { X1 = k.x[2]; X2 = k.x[3]; Y1 = y2; Y2 = y3; P1 = pm2; P2 = ypc1_end(s3, s3 + d3 * (s3 - s2) * k.r23); }
-    int err = 0;
-    double sig = sigs_interval(X2 - X1, Y1, Y2, P1, P2, err);
-    if (err == 0) return hval_interval(T, X1, X2, Y1, Y2, P1, P2, sig);
-    // linint fallback (interpolation_module.f90:25-59), n = 4
+    const double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
+    const double s1 = (y1 - y0) * k.r1, s2 = (y2 - y1) * k.r2, s3 = (y3 - y2) * k.r3;
+    const int I = (T < k.x[0]) ? 0 : (T > k.x[3]) ? 2 : (T < k.x[2] ? (T < k.x[1] ? 0 : 1) : 2);
+    // interior-knot slope needed by every case: knot 1 for I = 0,1; knot 2 for I = 2
+    const bool hi = I == 2;
+    const double mA = ypc1_mid_r(hi ? d2 : d1, hi ? d3 : d2, hi ? s2 : s1, hi ? s3 : s2, hi ? k.r23 : k.r12);
+    if (I == 0) { v.X1 = k.x[0]; v.X2 = k.x[1]; v.Y1 = y0; v.Y2 = y1; v.P1 = ypc1_end(s1, s1 + d1 * (s1 - s2) * k.r12); v.P2 = mA; }
+    else if (I == 1) { v.X1 = k.x[1]; v.X2 = k.x[2]; v.Y1 = y1; v.Y2 = y2; v.P1 = mA; v.P2 = ypc1_mid_r(d2, d3, s2, s3, k.r23); }
+    else { v.X1 = k.x[2]; v.X2 = k.x[3]; v.Y1 = y2; v.Y2 = y3; v.P1 = mA; v.P2 = ypc1_end(s3, s3 + d3 * (s3 - s2) * k.r23); }
+}
+LT_DEV double linint4(const Knots4& k, double y0, double y1, double y2, double y3, double T)
+{   // linint fallback when SigErr (interpolation_module.f90:25-59), n = 4
     const double Y[4] = {y0, y1, y2, y3};
     int jlo = 1, jhi = 4;
     for (;;) { int q = (jhi + jlo) / 2; if (k.x[q - 1] > T) jhi = q; else jlo = q; if (jhi - jlo == 1) break; }
@@ -120,12 +123,58 @@ LT_DEV void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st,
     const bool first = D.p == 1;                     // (b,b,c): the forward profile is not used
     if (!first) knots_prepare(kf);
     const double* w = v < 3 ? D.LW[v] : D.LW4;
+    // Phase A: evaluated interval + SIGS classification of all NF x 3 splines.
+    // Phase B: ONE Newton loop per lane over its pending convexity solves -- lanes work on
+    //          different splines but execute the same instructions (a loop per spline made the
+    //          warp pay a full solve per spline whenever any lane needed one).
+    // Phase C: HVAL.
+    constexpr int NS = NF * 3;
+    Iv4 iv[NS]; double sg[NS], tp[NS]; int pend[NS], np = 0; bool bad[NS];
+    const int nt = first ? 2 : 3;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        double pb = spline4_eval2(kb, vb[f][0], vb[f][1], vb[f][2], vb[f][3], P_zb);
-        double pc = spline4_eval2(kc, vc[f][0], vc[f][1], vc[f][2], vc[f][3], P_zc);
-        double pf = first ? 0.0 : spline4_eval2(kf, vf[f][0], vf[f][1], vf[f][2], vf[f][3], P_zf);
-        out[f] = lag(w, pb, pc, pf);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int q = f * 3 + t;
+            bad[q] = false; sg[q] = 0.0;
+            if (t >= nt) continue;
+            const Knots4& kk = t == 0 ? kb : (t == 1 ? kc : kf);
+            const double* y = t == 0 ? vb[f] : (t == 1 ? vc[f] : vf[f]);
+            const double Tq = t == 0 ? P_zb : (t == 1 ? P_zc : P_zf);
+            spline4_prepare(kk, y[0], y[1], y[2], y[3], Tq, iv[q]);
+            double sigma, TP1, SIG0; int e = 0;
+            if (sigs_classify(iv[q].X2 - iv[q].X1, iv[q].Y1, iv[q].Y2, iv[q].P1, iv[q].P2, sigma, TP1, SIG0, e)) sg[q] = sigma;
+            else { sg[q] = SIG0; tp[np] = TP1; pend[np] = q; ++np; }
+            if (e) bad[q] = true;
+        }
+    }
+    {
+        int cur = 0; NewtonState ns;
+        if (np > 0) newton_start(ns, tp[0], sg[pend[0]]);
+        while (cur < np) {
+            double o; int e = 0;
+            if (newton_step(ns, o, e)) {
+                sg[pend[cur]] = o; if (e) bad[pend[cur]] = true;
+                if (++cur < np) newton_start(ns, tp[cur], sg[pend[cur]]);
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        double pv[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int q = f * 3 + t;
+            if (t >= nt) continue;
+            const double Tq = t == 0 ? P_zb : (t == 1 ? P_zc : P_zf);
+            if (!bad[q]) pv[t] = hval_interval(Tq, iv[q].X1, iv[q].X2, iv[q].Y1, iv[q].Y2, iv[q].P1, iv[q].P2, sg[q]);
+            else {
+                const Knots4& kk = t == 0 ? kb : (t == 1 ? kc : kf);
+                const double* y = t == 0 ? vb[f] : (t == 1 ? vc[f] : vf[f]);
+                pv[t] = linint4(kk, y[0], y[1], y[2], y[3], Tq);
+            }
+        }
+        out[f] = lag(w, pv[0], pv[1], pv[2]);
     }
 }
 
@@ -464,6 +513,7 @@ struct VtCtx {
     double hs[3];                         // newx spacing per hydro time (:120-124)
     double Z1, ZN, H, rH;                 // time-combined knot line: x(k) = Z1 + (k - 0.5) H
     double fy[VW], yp[VW], sg[VW];        // knot value, YPC1 slope, SIGS tension of interval (k, k+1)
+    double tp[VW]; unsigned char pend[VW]; // pending convexity solves of build()
     int ka, kb, ia, ib;                   // knots [ka, kb] held; intervals [ia, ib] fully defined
     bool sigerr;
     LT_DEV VtCtx(const LtDev& D_) : D(D_) {}
@@ -531,10 +581,23 @@ struct VtCtx {
         }
         // SIGS (tension:314-782) for every interval with both slopes known
         ia = pa; ib = pb - 1;
+        int np = 0;
         for (int k = ia; k <= ib; ++k) {
-            int e = 0;
-            sg[k - ka] = sigs_interval(knot_x(k + 1) - knot_x(k), fy[k - ka], fy[k + 1 - ka], yp[k - ka], yp[k + 1 - ka], e);
+            double sigma, TP1, SIG0; int e = 0;
+            if (sigs_classify(knot_x(k + 1) - knot_x(k), fy[k - ka], fy[k + 1 - ka], yp[k - ka], yp[k + 1 - ka], sigma, TP1, SIG0, e))
+                sg[k - ka] = sigma;
+            else { sg[k - ka] = SIG0; tp[np] = TP1; pend[np] = (unsigned char)(k - ka); ++np; }
             if (e) sigerr = true;
+        }
+        // one Newton loop per lane over all its pending intervals (see wcts2)
+        int cur = 0; NewtonState ns;
+        if (np > 0) newton_start(ns, tp[0], sg[pend[0]]);
+        while (cur < np) {
+            double o; int e = 0;
+            if (newton_step(ns, o, e)) {
+                sg[pend[cur]] = o; if (e) sigerr = true;
+                if (++cur < np) newton_start(ns, tp[cur], sg[pend[cur]]);
+            }
         }
     }
     // HVAL / HPVAL interval choice incl. INTRVL (tension:1026-1041, 1287-1354)
