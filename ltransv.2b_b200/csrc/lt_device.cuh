@@ -305,6 +305,28 @@ LT_DEV void snhcsh(double X, double& SINHM, double& COSHM, double& COSHMM)
 // SIGMA zeroed on entry), so solving only the interval that is evaluated gives the
 // value the reference's full sweep stores for it.  err = 1 <=> NIT > 10000 (SigErr).
 #define LT_RTOL (200.0 * 1.1102230246251565e-16)      /* 200 * 2^-53, the :433-439 loop */
+// Initial guess of the convexity equation's root.  The root of  s (cosh s - 1)/(sinh s - s) = T + 1
+// is a function of T alone; g_sigtab holds root(x)/x on x = sqrt(10 T - 20) in [0, 32] (x is the
+// reference's own starting value, exact to leading order as T -> 2), filled by ltgpu_create.
+// Starting Newton ~1e-7 from the root instead of 5-50 % away cuts the iterations from 5-7 to
+// 2-3; the stopping rule, the NIT cap and therefore the converged value are the reference's.
+#define LT_SIGTAB_N 8192
+#define LT_SIGTAB_INV_H 256.0
+__device__ double g_sigtab[LT_SIGTAB_N + 1];
+LT_DEV double sig_guess(double T)
+{
+    double x = sqrt(10.0 * T - 20.0);
+#ifdef LT_IEEE_DIV
+    return x;
+#else
+    double u = x * LT_SIGTAB_INV_H;
+    if (!(u < (double)LT_SIGTAB_N)) return T + 1.0;
+    int i = (int)u; double f = u - (double)i;
+    double c0 = g_sigtab[i], c1 = g_sigtab[i + 1];
+    return x * (c0 + f * (c1 - c0));
+#endif
+}
+
 // One Newton iteration of the convexity equation  SIG * T1(SIG) = TP1  (tension:528-579).
 // Returns true when the loop of the reference would exit; `out` is then the tension factor
 // (0 with err = 1 when the reference would raise SigErr).  State: SIG, NIT, chk, chk_at.
@@ -359,7 +381,7 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
         double T = fmax(qdiv(D1, D2), qdiv(D2, D1));
         if (T <= 2.0) { sigma = 0.0; return true; }
         TP1o = T + 1.0;
-        SIG0 = sqrt(10.0 * T - 20.0);
+        SIG0 = sig_guess(T);                               // reference: SQRT(10 T - 20) (tension:524)
         return false;
     }
     // monotonicity :638-760

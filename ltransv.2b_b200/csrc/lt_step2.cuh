@@ -102,6 +102,19 @@ LT_DEV double linint4(const Knots4& k, double y0, double y1, double y2, double y
     return m * T + (Y[jlo - 1] - m * k.x[jlo - 1]);
 }
 
+// TSPSI(N=4) + HVAL (or the linint fallback) at T: the water-column profile value of
+// WCTS_ITPI (hydro:2619-2644).  Flattening the Newton solves of the 9 splines of one
+// find_currents into one loop (as VtCtx::build does) was tried and lost: the per-spline
+// state it has to keep (9 x 7 doubles) spills, see profiles/r01_notes.md.
+LT_DEVN double spline4_eval2(const Knots4& k, double y0, double y1, double y2, double y3, double T)
+{
+    Iv4 v; spline4_prepare(k, y0, y1, y2, y3, T, v);
+    int err = 0;
+    double sig = sigs_interval(v.X2 - v.X1, v.Y1, v.Y2, v.P1, v.P2, err);
+    if (err == 0) return hval_interval(T, v.X1, v.X2, v.Y1, v.Y2, v.P1, v.P2, sig);
+    return linint4(k, y0, y1, y2, y3, T);
+}
+
 struct Stage2 { Stencil r, u, v; };
 
 // WCTS_ITPI (hydro:2577-2689) for NF fields sharing one set of knots (u and v share the
@@ -123,58 +136,12 @@ LT_DEV void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st,
     const bool first = D.p == 1;                     // (b,b,c): the forward profile is not used
     if (!first) knots_prepare(kf);
     const double* w = v < 3 ? D.LW[v] : D.LW4;
-    // Phase A: evaluated interval + SIGS classification of all NF x 3 splines.
-    // Phase B: ONE Newton loop per lane over its pending convexity solves -- lanes work on
-    //          different splines but execute the same instructions (a loop per spline made the
-    //          warp pay a full solve per spline whenever any lane needed one).
-    // Phase C: HVAL.
-    constexpr int NS = NF * 3;
-    Iv4 iv[NS]; double sg[NS], tp[NS]; int pend[NS], np = 0; bool bad[NS];
-    const int nt = first ? 2 : 3;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int q = f * 3 + t;
-            bad[q] = false; sg[q] = 0.0;
-            if (t >= nt) continue;
-            const Knots4& kk = t == 0 ? kb : (t == 1 ? kc : kf);
-            const double* y = t == 0 ? vb[f] : (t == 1 ? vc[f] : vf[f]);
-            const double Tq = t == 0 ? P_zb : (t == 1 ? P_zc : P_zf);
-            spline4_prepare(kk, y[0], y[1], y[2], y[3], Tq, iv[q]);
-            double sigma, TP1, SIG0; int e = 0;
-            if (sigs_classify(iv[q].X2 - iv[q].X1, iv[q].Y1, iv[q].Y2, iv[q].P1, iv[q].P2, sigma, TP1, SIG0, e)) sg[q] = sigma;
-            else { sg[q] = SIG0; tp[np] = TP1; pend[np] = q; ++np; }
-            if (e) bad[q] = true;
-        }
-    }
-    {
-        int cur = 0; NewtonState ns;
-        if (np > 0) newton_start(ns, tp[0], sg[pend[0]]);
-        while (cur < np) {
-            double o; int e = 0;
-            if (newton_step(ns, o, e)) {
-                sg[pend[cur]] = o; if (e) bad[pend[cur]] = true;
-                if (++cur < np) newton_start(ns, tp[cur], sg[pend[cur]]);
-            }
-        }
-    }
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        double pv[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int q = f * 3 + t;
-            if (t >= nt) continue;
-            const double Tq = t == 0 ? P_zb : (t == 1 ? P_zc : P_zf);
-            if (!bad[q]) pv[t] = hval_interval(Tq, iv[q].X1, iv[q].X2, iv[q].Y1, iv[q].Y2, iv[q].P1, iv[q].P2, sg[q]);
-            else {
-                const Knots4& kk = t == 0 ? kb : (t == 1 ? kc : kf);
-                const double* y = t == 0 ? vb[f] : (t == 1 ? vc[f] : vf[f]);
-                pv[t] = linint4(kk, y[0], y[1], y[2], y[3], Tq);
-            }
-        }
-        out[f] = lag(w, pv[0], pv[1], pv[2]);
+        double pb = spline4_eval2(kb, vb[f][0], vb[f][1], vb[f][2], vb[f][3], P_zb);
+        double pc = spline4_eval2(kc, vc[f][0], vc[f][1], vc[f][2], vc[f][3], P_zc);
+        double pf = first ? 0.0 : spline4_eval2(kf, vf[f][0], vf[f][1], vf[f][2], vf[f][3], P_zf);
+        out[f] = lag(w, pb, pc, pf);
     }
 }
 

@@ -235,6 +235,28 @@ static void fill_all(ltgpu_ctx* ctx, const uint8_t* dbase, const size_t off[7], 
     }
 }
 
+// ---- table of root(x)/x for the SIGS convexity equation (lt_device.cuh::sig_guess) -----
+static double convexity_G(double s)
+{   // s (cosh s - 1) / (sinh s - s), accurate for all s > 0
+    if (s < 0.3) {  // series: numerator s^3/2 (1 + s^2/12 + ...), denominator s^3/6 (1 + s^2/20 + ...)
+        double s2 = s * s, num = 0.0, den = 0.0, tn = 0.5, td = 1.0 / 6.0;
+        for (int k = 0; k < 12; ++k) { num += tn; den += td; tn *= s2 / ((2 * k + 3) * (2 * k + 4)); td *= s2 / ((2 * k + 4) * (2 * k + 5)); }
+        return num / den;
+    }
+    double sh2 = sinh(0.5 * s);
+    return s * (2.0 * sh2 * sh2) / (sinh(s) - s);
+}
+static void build_sigtab(std::vector<double>& tab)
+{
+    tab.assign(LT_SIGTAB_N + 1, 1.0);
+    for (int i = 1; i <= LT_SIGTAB_N; ++i) {
+        double x = (double)i / LT_SIGTAB_INV_H, target = 3.0 + x * x / 10.0;      // T + 1
+        double lo = 0.0, hi = target + 1.0;                                        // G(s) >= s - ... and G(0+) = 3
+        for (int it = 0; it < 200; ++it) { double mid = 0.5 * (lo + hi); if (convexity_G(mid) < target) lo = mid; else hi = mid; }
+        tab[i] = 0.5 * (lo + hi) / x;
+    }
+}
+
 // ---- exact spatial indices over the boundary tables (used by k_finish) ----------------
 // The bucket / band of a coordinate is floor((v - origin) * scale) in IEEE double on both
 // host and device; that map is monotone, which is all the exactness argument needs.
@@ -397,6 +419,11 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     ctx->nthreads_grid = pr.multiProcessorCount * 1024;
     if (cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LTGPU_E_CUDA; }
+    {
+        static std::vector<double> tab;
+        if (tab.empty()) build_sigtab(tab);
+        if (cudaMemcpyToSymbol(g_sigtab, tab.data(), sizeof(double) * tab.size()) != cudaSuccess) { delete ctx; return LTGPU_E_CUDA; }
+    }
     for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->slot_ready[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->slot_free, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->stage_done[i], cudaEventDisableTiming);
