@@ -1,0 +1,80 @@
+"""Host-side formats and run loop: the namelist
+reader, CSV inputs, Fortran-formatted outputs and the external/internal loop with print
+intervals.  The CPU oracle stands in for the engine here; the GPU counterpart is in
+tests/test_parity_gpu.py::test_driver_outputs_match."""
+import os
+import re
+
+import numpy as np
+
+from common import ROOT, SMALL, World, make_params
+from ltrans_b200.host import formats
+from ltrans_b200.host.driver import Run
+
+
+def test_namelist_reader_matches_shipped_defaults():
+    nml = formats.read_namelist(os.path.join(ROOT, "tests", "golden", "LTRANS_sample.data"))
+    assert list(nml)[:4] == ["numparticles", "timeparam", "hydroparam", "turbparam"]
+    assert nml["timeparam"] == {"days": 4.5, "iprint": 3600, "dt": 3600, "idt": 120}
+    assert nml["output"]["outpath"] == "./output/" and nml["parloc"]["parfile"].endswith(".csv")
+    p, flat = formats.params_from_namelist(nml)
+    from ltrans_b200.host.binding import Params
+    q = Params.shipped()
+    for name, _ in Params._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+    assert flat["pi"] == 3.14159265358979 and flat["latmin"] == 36
+
+
+def test_namelist_reader_crlf_and_ampersand_groups(tmp_path):
+    f = tmp_path / "x.data"
+    f.write_bytes(b"&timeparam\r\n  dt = 1800 ! c\r\n  days=2.d0\r\n/\r\n$other\r\n FreeSlip=.T.\r\n$end\r\n")
+    nml = formats.read_namelist(str(f))
+    assert nml == {"timeparam": {"dt": 1800, "days": 2.0}, "other": {"freeslip": True}}
+
+
+def test_fortran_edit_descriptors():
+    assert formats._F(-12.3456, 10, 3) == "   -12.346" and formats._F(0.5, 9, 4) == "   0.5000"
+    assert formats._I(-3, 7) == "     -3" and formats._I(12345678, 7) == "*******"
+    assert formats._F(123456.0, 8, 4) == "********"
+    assert formats.para_filename(2, "out") == os.path.join("out", "para10000002.csv")
+
+
+def test_particle_csv_round_trip(tmp_path):
+    lon = np.array([-76.01, -75.9]); lat = np.array([37.0, 37.2]); z = np.array([-3.5, -0.25]); dob = np.array([0.0, 3600.0])
+    p = str(tmp_path / "Initial_particle_locations.csv")
+    formats.write_particles_csv(p, lon, lat, z, dob, np.array([101001, 101002]))
+    a = formats.read_particles_csv(p, True)
+    assert np.allclose(a[0], lon) and np.allclose(a[2], z) and list(a[4]) == [101001, 101002]
+    assert list(formats.read_particles_csv(p, False)[4]) == [0, 0]
+
+
+def run_driver(engine, outdir, n=120, **kw):
+    w = World(**SMALL)
+    base = dict(Behavior=4, HTurbOn=1, VTurbOn=0, pediage=3600.0, deadage=9000.0, SaltTempOn=1,
+                TrackCollisions=1, ErrorFlag=1)
+    base.update(kw)
+    prm = make_params(w, n, **base)
+    x, y, z, dob, r, u, v = w.seed_particles(n, seed=77)
+    lon, lat = w.proj.x2lon(x, y), w.proj.y2lat(y)
+    run = Run(engine, w, prm, outdir, days=3 / 24.0, iprint=1800)
+    run.init(lon, lat, z, dob, startpoly=np.full(n, 101001, np.int32))
+    f = run.run()
+    return run, f
+
+
+def test_run_loop_writes_reference_formats(tmp_path):
+    from oracle.oracle import Oracle
+    out = str(tmp_path / "o")
+    run, f = run_driver(Oracle(), out)
+    files = sorted(os.listdir(out))
+    # 3 h at iprint = 1800 s -> 6 prints, first file para10000002.csv
+    assert [x for x in files if x.startswith("para")] == ["para1000000%d.csv" % k for k in range(2, 8)]
+    row = re.compile(r"^ *-?\d+\.\d{3}, *-?\d+, *-?\d+\.\d{4}, *-?\d+\.\d{4}, *-?\d+\.\d{4}, *-?\d+\.\d{4}$")
+    lines = open(os.path.join(out, "para10000007.csv")).read().splitlines()
+    assert len(lines) == 120 and all(row.match(s) and len(s) == 10 + 8 + 10 + 10 + 9 + 9 for s in lines)
+    end = open(os.path.join(out, "endfile.csv")).read().splitlines()
+    assert len(end) == 120 and all(len(s.split(",")) == 6 for s in end)
+    st = np.array([int(s.split(",")[2]) for s in end])
+    assert set(st) <= {4, 2, -1, -2, -3} and (st == -2).sum() == (f["status"] == -2).sum()
+    hits = open(os.path.join(out, "LandHits.csv")).read().splitlines()
+    assert hits[0].startswith("numpar") and all(len(s.split(",")) == 7 for s in hits[1:])

@@ -169,3 +169,54 @@ def test_full_size_properties():
     assert np.all(fa["age"][act] == 6 * prm.idt)
     moved = np.hypot(fa["x"] - x, fa["y"] - y)[act]
     assert 1.0 < np.median(moved) < 6 * prm.idt * 1.5
+
+
+def test_driver_outputs_match(tmp_path):
+    """Whole pipeline (run loop, print intervals, para*.csv / endfile.csv / hit files) with the
+    CUDA engine vs the oracle engine: same files, same numbers."""
+    from oracle.oracle import Oracle
+    from test_formats import run_driver
+    og, oo = str(tmp_path / "gpu"), str(tmp_path / "ora")
+    run_driver(LtransLib(), og)
+    run_driver(Oracle(), oo)
+    assert sorted(os.listdir(og)) == sorted(os.listdir(oo))
+    for name in sorted(os.listdir(og)):
+        if name.startswith("para") or name == "endfile.csv":
+            a = np.loadtxt(os.path.join(og, name), delimiter=","); b = np.loadtxt(os.path.join(oo, name), delimiter=",")
+            assert a.shape == b.shape and np.allclose(a, b, rtol=0, atol=1.01e-3), name
+            assert np.mean(a == b) > 0.999, name
+        else:
+            assert open(os.path.join(og, name)).read().splitlines()[0] == open(os.path.join(oo, name)).read().splitlines()[0]
+
+
+GULF = dict(ni=48, nj=40, us=36, hmin=40.0, hmax=600.0, dlon=0.02, dlat=0.018, speed=0.9)
+
+
+def test_gulf_like_buoyant_particles_turbulence_off():
+    """BASELINE configs[3] shape at test size: us 36 / ws 37, deep water, Behavior 6 with a positive
+    `sink` (buoyant droplets), open ocean boundary."""
+    rg, ro, res, ev, st, fg, fo = _pair(600, 3, world_kw=GULF, **dict(PASSIVE, Behavior=6, sink=0.002, swimstart=0.0,
+                                                                       HTurbOn=1, OpenOceanBoundary=1))
+    assert rg == ro
+    assert_parity(res, 1e-9)
+    assert np.array_equal(st[0], st[1])
+
+
+def test_gulf_like_vturb_windows():
+    """ws = 37 -> 148 spline knots: the 32-knot window of k_vturb is re-centred by many particles."""
+    rg, ro, res, ev, st, fg, fo = _pair(1500, 1, nint=3, world_kw=GULF, **dict(PASSIVE, Behavior=6, sink=0.002, HTurbOn=1, VTurbOn=1))
+    dz = np.abs(fg["z"] - fo["z"]) / 600.0
+    assert np.mean(dz <= 1e-9) >= 0.99 and np.median(dz) <= 1e-14, (float(np.mean(dz <= 1e-9)), float(np.median(dz)))
+    assert res["n_status"] == 0 and res["n_r_ele"] == 0
+
+
+def test_oyster_run_with_turbulence_statistics():
+    """BASELINE configs[2] shape at test size: Behavior 4 (C. virginica), HTurb + VTurb, settlement
+    polygons with holes, mortality.  Same Philox stream; compared in distribution."""
+    from scipy import stats as ss
+    rg, ro, res, ev, st, fg, fo = _pair(3000, 3, **dict(Behavior=4, HTurbOn=1, VTurbOn=1, pediage=3600.0, deadage=9000.0))
+    assert rg == ro
+    assert np.abs(st[0][:3] - st[1][:3]).max() <= max(3, 0.01 * 3000), (st[0], st[1])      # settled, dead, out of bounds
+    assert np.mean(fg["status"] == fo["status"]) >= 0.99
+    assert ss.ks_2samp(fg["z"], fo["z"]).pvalue > 0.1
+    assert np.mean(np.abs(fg["x"] - fo["x"]) <= 1e-6 * 1.4e4) >= 0.95
