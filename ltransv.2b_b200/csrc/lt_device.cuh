@@ -143,7 +143,10 @@ LT_DEVN bool gridcell(const double* __restrict__ q, double X, double Y)
 // setEle (hydro:1414-1532), neighbour-search form.  Returns false for "jumped over
 // an element" (a 0 entry reached, ledger 17).  If all 10 entries are non-zero and none
 // matches, the reference raises nothing and keeps the old element (hydro:1464-1476).
-LT_DEV bool find_element(const LtGridTab& G, double X, double Y, int& ele)
+#ifndef LT_FE_ATTR
+#define LT_FE_ATTR LT_DEVN
+#endif
+LT_FE_ATTR bool find_element(const LtGridTab& G, double X, double Y, int& ele)
 {
     const int* row = G.adj + (size_t)(ele - 1) * 10;
     for (int i = 0; i < 10; ++i) {
@@ -163,7 +166,7 @@ struct Wt { int mode; double t, u, w2, w3; };
 // triangles keeps tOK = 2), interp (hydro:2533-2565) otherwise.  The weights are a function
 // of (element, point) only: the reference recomputes them for every interpolated value
 // (36 times per RK stage); here once per (grid, stage).
-LT_DEV Wt make_weights(const double* __restrict__ q, double xp, double yp, bool setinterp_quirk)
+LT_DEVN Wt make_weights(const double* __restrict__ q, double xp, double yp, bool setinterp_quirk)
 {
     double x1 = q[0], x2 = q[1], x3 = q[2], x4 = q[3], y1 = q[4], y2 = q[5], y3 = q[6], y4 = q[7];
     Wt w; w.w2 = 0.0; w.w3 = 0.0;
@@ -232,32 +235,46 @@ struct Stencil {            // element corner nodes + coordinates + weights at o
     int4 nd; const double* q; Wt w; double xp, yp;
 };
 
+// getInterp (hydro:1743-2005) / interp (hydro:2008-2569) with precomputed weights.
+// free-slip substitution on the three time levels of one stencil (kept out of line: it is off
+// in the shipped configuration and would otherwise be inlined into every gather)
+LT_DEVN void gather_freeslip(const LtDev& D, double* b, double* c, double* f, int4 nd, int grid, int4 und)
+{
+    const uint8_t* mk = grid == G_RHO ? D.R.mask : grid == G_U ? D.U.mask : D.V.mask;
+    int m[4] = { mk[nd.x], mk[nd.y], mk[nd.z], mk[nd.w] }, md[4];
+    md[0] = m[0]; md[1] = m[1]; md[2] = m[2]; md[3] = m[3];
+    if (grid == G_V) {   // v_mask(unode*) in the diagonal test (hydro:2500-2503); out of range -> water
+        int nv = D.V.nodes;
+        md[0] = und.x < nv ? D.V.mask[und.x] : 1; md[1] = und.y < nv ? D.V.mask[und.y] : 1;
+        md[2] = und.z < nv ? D.V.mask[und.z] : 1; md[3] = und.w < nv ? D.V.mask[und.w] : 1;
+    }
+    int one = grid == G_U ? 1 : 3;                       // hydro:2408
+    freeslip(b, m, one, md); freeslip(c, m, one, md); freeslip(f, m, one, md);
+}
+
 // value of one (field, level) at the three hydro times: the 4-corner gather of
 // getInterp (hydro:1743-2005) / interp (hydro:2008-2569) with precomputed weights.
+// Out of line on purpose: ~16 call sites per kernel; inlined they made k_advect 15 k SASS
+// instructions and instruction fetch its top stall (profiles/r01_notes.md).
 template <class T, int PH>
-LT_DEV void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
-                       double& rb, double& rc, double& rf)
+LT_DEV void gather_bcf_inl(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
+                           double& rb, double& rc, double& rf)
 {
     double b[4], c[4], f[4];
     LoadBCF<T, PH>::get(fld, (size_t)s.nd.x * L + lev0, b[0], c[0], f[0]);
     LoadBCF<T, PH>::get(fld, (size_t)s.nd.y * L + lev0, b[1], c[1], f[1]);
     LoadBCF<T, PH>::get(fld, (size_t)s.nd.z * L + lev0, b[2], c[2], f[2]);
     LoadBCF<T, PH>::get(fld, (size_t)s.nd.w * L + lev0, b[3], c[3], f[3]);
-    if (D.P.FreeSlip) {
-        const uint8_t* mk = grid == G_RHO ? D.R.mask : grid == G_U ? D.U.mask : D.V.mask;
-        int m[4] = { mk[s.nd.x], mk[s.nd.y], mk[s.nd.z], mk[s.nd.w] }, md[4];
-        md[0] = m[0]; md[1] = m[1]; md[2] = m[2]; md[3] = m[3];
-        if (grid == G_V) {   // v_mask(unode*) in the diagonal test (hydro:2500-2503); out of range -> water
-            int nv = D.V.nodes;
-            md[0] = und.x < nv ? D.V.mask[und.x] : 1; md[1] = und.y < nv ? D.V.mask[und.y] : 1;
-            md[2] = und.z < nv ? D.V.mask[und.z] : 1; md[3] = und.w < nv ? D.V.mask[und.w] : 1;
-        }
-        int one = grid == G_U ? 1 : 3;                       // hydro:2408
-        freeslip(b, m, one, md); freeslip(c, m, one, md); freeslip(f, m, one, md);
-    }
+    if (D.P.FreeSlip) gather_freeslip(D, b, c, f, s.nd, grid, und);
     rb = combine(s.w, b[0], b[1], b[2], b[3]);
     rc = combine(s.w, c[0], c[1], c[2], c[3]);
     rf = combine(s.w, f[0], f[1], f[2], f[3]);
+}
+template <class T, int PH>
+LT_DEVN void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
+                        double& rb, double& rc, double& rf)
+{
+    gather_bcf_inl<T, PH>(D, fld, L, lev0, s, grid, und, rb, rc, rf);
 }
 
 LT_DEV double gather_static(const LtDev& D, const double* arr, const Stencil& s)
@@ -539,6 +556,8 @@ LT_DEV double box_muller(const LtDev& D, unsigned w1, unsigned w2)
 {
     return sqrt(-2.0 * log(u_real3(w1))) * cos(2.0 * D.P.PI * u_real3(w2));
 }
+LT_DEVN double box_muller_n(const LtDev& D, unsigned w1, unsigned w2) { return box_muller(D, w1, w2); }
+LT_DEVN double log10_n(double x) { return log10(x); }
 
 // -------------------------------------------------------------- boundary ----
 struct Hit { double ix, iy, rx, ry; int seg; bool water; };

@@ -119,8 +119,11 @@ struct Stage2 { Stencil r, u, v; };
 
 // WCTS_ITPI (hydro:2577-2689) for NF fields sharing one set of knots (u and v share the
 // rho-level knots).  v = 0,1,2: value at ix(v+1); v = 3: (b + 4c + f)/6.
+#ifndef LT_WCTS_ATTR
+#define LT_WCTS_ATTR LT_DEV
+#endif
 template <class T, int PH, bool W, int NF>
-LT_DEV void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st, const int* grid, int4 und, int L,
+LT_WCTS_ATTR void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st, const int* grid, int4 und, int L,
                   const ColK& col, int deplvl, double P_zb, double P_zc, double P_zf, int v, double* out)
 {
     double vb[NF][4], vc[NF][4], vf[NF][4];
@@ -164,12 +167,12 @@ LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, do
         gather_bcf<T, PH>(D, fv, us, 0, s.v, G_V, s.u.nd, Vb, Vc, Vf);
         gather_bcf<T, PH>(D, fw, ws, 1, s.r, G_RHO, s.u.nd, Wb, Wc, Wf);
         double rz0 = qrcp(z0);
-        double num = log10((Zpar - wzb1) * rz0);
+        double num = log10_n((Zpar - wzb1) * rz0);
         double wzb2, wzc2, wzf2; zlev3<true>(D, col, 1, wzb2, wzc2, wzf2);
-        double db = num * qrcp(log10((zb1 - wzb1) * rz0)), dc = num * qrcp(log10((zc1 - wzb1) * rz0)),
-               df = num * qrcp(log10((zf1 - wzb1) * rz0));
-        double wb = num * qrcp(log10((wzb2 - wzb1) * rz0)), wc = num * qrcp(log10((wzc2 - wzb1) * rz0)),
-               wf = num * qrcp(log10((wzf2 - wzb1) * rz0));
+        double db = num * qrcp(log10_n((zb1 - wzb1) * rz0)), dc = num * qrcp(log10_n((zc1 - wzb1) * rz0)),
+               df = num * qrcp(log10_n((zf1 - wzb1) * rz0));
+        double wb = num * qrcp(log10_n((wzb2 - wzb1) * rz0)), wc = num * qrcp(log10_n((wzc2 - wzb1) * rz0)),
+               wf = num * qrcp(log10_n((wzf2 - wzb1) * rz0));
         Uad = lag(lw, Ub * db, Uc * dc, Uf * df);
         Vad = lag(lw, Vb * db, Vc * dc, Vf * df);
         Wad = lag(lw, Wb * wb, Wc * wc, Wf * wf);
@@ -450,8 +453,8 @@ LT_DEV void advect_particle(const LtDev& D, int n)
         Rng g = make_rng(D, n);
         uint4 r = philox(g, 0u);
         double sd = sqrt(2.0 * P.ConstantHTurb * idt);
-        newX = (Xpar + idt * (P_U * ca - P_V * sa)) + box_muller(D, r.x, r.y) * sd;
-        newY = (Ypar + idt * (P_U * sa + P_V * ca)) + box_muller(D, r.z, r.w) * sd;
+        newX = (Xpar + idt * (P_U * ca - P_V * sa)) + box_muller_n(D, r.x, r.y) * sd;
+        newY = (Ypar + idt * (P_U * sa + P_V * ca)) + box_muller_n(D, r.z, r.w) * sd;
     }
     D.s_depth[n] = P_depth; D.s_angle[n] = P_angle;
     D.s_zeb[n] = P_zetab; D.s_zec[n] = P_zetac; D.s_zef[n] = P_zetaf;
@@ -597,7 +600,7 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     const T* fk = (const T*)D.kh;
 #pragma unroll 1
     for (int l = 0; l < V.ws; ++l) {
-        gather_bcf<T, PH>(D, fk, V.ws, l, s0, G_RHO, s0.nd, V.khp[0][l], V.khp[1][l], V.khp[2][l]);
+        gather_bcf_inl<T, PH>(D, fk, V.ws, l, s0, G_RHO, s0.nd, V.khp[0][l], V.khp[1][l], V.khp[2][l]);
         zlev3<true>(D, col, l, V.zl[0][l], V.zl[1][l], V.zl[2][l]);
     }
     const double rp2 = 1.0 / (double)V.p2;
@@ -612,24 +615,33 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     const int loop = D.P.idt / 2;                                       // :282-283
     double ParZc = P_zc;
     uint4 rnd = make_uint4(0, 0, 0, 0);
+    // the current interval's seven numbers live in registers; the thread-local knot arrays
+    // are only touched when the particle changes interval (long-scoreboard stalls on those
+    // arrays were k_vturb's top stall)
+    int cI = -1; double cX1 = 0, cX2 = 0, cY1 = 0, cY2 = 0, cP1 = 0, cP2 = 0, cSG = 0;
+    auto load_iv = [&](double zq) {
+        if (cI >= 0 && zq >= cX1 && zq < cX2) return;                  // still inside [X(I), X(I+1)): INTRVL gives I
+        int I = V.interval(zq); V.need(I);
+        int q = I - V.ka;
+        cI = I; cX1 = V.knot_x(I); cX2 = V.knot_x(I + 1);
+        cY1 = V.fy[q]; cY2 = V.fy[q + 1]; cP1 = V.yp[q]; cP2 = V.yp[q + 1]; cSG = V.sg[q];
+    };
 #pragma unroll 1
     for (int i = 0; i < loop; ++i) {                                    // :291-337
         double Kprimec = 0.0;
         if (!(ParZc < P_depth || ParZc > P_zetac)) {
-            int I = V.interval(ParZc); V.need(I);
-            int q = I - V.ka; const double X1 = V.knot_x(I), X2 = V.knot_x(I + 1);
-            if (!V.sigerr) Kprimec = hpval_interval(ParZc, X1, X2, V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
-            else Kprimec = qdiv(V.fy[q] - V.fy[q + 1], X1 - X2);       // linint slope
+            load_iv(ParZc);
+            if (!V.sigerr) Kprimec = hpval_interval(ParZc, cX1, cX2, cY1, cY2, cP1, cP2, cSG);
+            else Kprimec = qdiv(cY1 - cY2, cX1 - cX2);                  // linint slope
         }
         const double KprimeZc = -1.0 * Kprimec * deltat;
         const double Z3rdc = ParZc + 0.5 * KprimeZc;
         double KH3rdc;
         if (Z3rdc < P_depth || Z3rdc > P_zetac) KH3rdc = background;
         else {
-            int I = V.interval(Z3rdc); V.need(I);
-            int q = I - V.ka; const double X1 = V.knot_x(I), X2 = V.knot_x(I + 1);
-            if (!V.sigerr) KH3rdc = hval_interval(Z3rdc, X1, X2, V.fy[q], V.fy[q + 1], V.yp[q], V.yp[q + 1], V.sg[q]);
-            else { double m = qdiv(V.fy[q] - V.fy[q + 1], X1 - X2); KH3rdc = m * Z3rdc + (V.fy[q] - m * X1); }
+            load_iv(Z3rdc);
+            if (!V.sigerr) KH3rdc = hval_interval(Z3rdc, cX1, cX2, cY1, cY2, cP1, cP2, cSG);
+            else { double m = qdiv(cY1 - cY2, cX1 - cX2); KH3rdc = m * Z3rdc + (cY1 - m * cX1); }
             if (KH3rdc < background) KH3rdc = background;
         }
         if ((i & 1) == 0) rnd = philox(g, 1u + (unsigned)(i >> 1));
