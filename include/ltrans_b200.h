@@ -46,8 +46,20 @@ extern "C" {
 #define LTGPU_EV_JUMP_V         29  /*                             (:1359)     */
 
 /* ---- RNG modes --------------------------------------------------------- */
-#define LTGPU_RNG_PHILOX    1   /* Philox4x32-10, key=(seed,0),                */
-                                /* counter=(particle id, step, block, 0)       */
+/* The reference draws from one global sequential Mersenne Twister
+ * (random_module.f90), so its turbulent trajectories depend on particle order and
+ * count.  The device uses a counter-based stream instead:
+ *   Philox4x32-10, key = (seed, 0),
+ *   counter = (particle id low 32, id high 32, global internal step, block)
+ *     global internal step = (p - 1) * (dt / idt) + it          (1-based)
+ *     block 0              : HTurb, words 0,1 -> x deviate; 2,3 -> y deviate
+ *     block 1 + i/2        : VTurb sub-step i (0-based), words 2(i%2), 2(i%2)+1
+ *     block 0x80000000     : behave, words 0,1,2 in draw order
+ *   uniforms: genrand_real3 = (w + 0.5)/2^32, genrand_real1 = w/(2^32 - 1)
+ *   (random_module.f90:239-246, 213-220); norm() = sqrt(-2 ln u1) cos(2 PI u2)
+ *   with the namelist PI (norm_module.f90:25-39).
+ * particle id = first_id + local index, so results do not depend on sharding. */
+#define LTGPU_RNG_PHILOX    1
 
 /* field storage on the device */
 #define LTGPU_F32           4   /* ROMS history is float32: lossless           */

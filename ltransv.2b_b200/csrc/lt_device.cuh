@@ -277,6 +277,32 @@ LT_DEVN void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Ste
     gather_bcf_inl<T, PH>(D, fld, L, lev0, s, grid, und, rb, rc, rf);
 }
 
+// Four consecutive levels of one field at the three hydro times (the 4-knot profile of
+// WCTS_ITPI, hydro:2603-2610).  With the [node][level][slot] layout the four levels of a
+// corner are 64 contiguous bytes (f32), and all 16 vector loads are issued before the first
+// use, so one memory latency is exposed per profile instead of one per level.
+template <class T, int PH>
+LT_DEVN void gather4_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
+                         double* __restrict__ vb, double* __restrict__ vc, double* __restrict__ vf)
+{
+    double b[4][4], c[4][4], f[4][4];           // [level][corner]
+    const size_t n0 = (size_t)s.nd.x * L + lev0, n1 = (size_t)s.nd.y * L + lev0, n2 = (size_t)s.nd.z * L + lev0, n3 = (size_t)s.nd.w * L + lev0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        LoadBCF<T, PH>::get(fld, n0 + i, b[i][0], c[i][0], f[i][0]);
+        LoadBCF<T, PH>::get(fld, n1 + i, b[i][1], c[i][1], f[i][1]);
+        LoadBCF<T, PH>::get(fld, n2 + i, b[i][2], c[i][2], f[i][2]);
+        LoadBCF<T, PH>::get(fld, n3 + i, b[i][3], c[i][3], f[i][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (D.P.FreeSlip) gather_freeslip(D, b[i], c[i], f[i], s.nd, grid, und);
+        vb[i] = combine(s.w, b[i][0], b[i][1], b[i][2], b[i][3]);
+        vc[i] = combine(s.w, c[i][0], c[i][1], c[i][2], c[i][3]);
+        vf[i] = combine(s.w, f[i][0], f[i][1], f[i][2], f[i][3]);
+    }
+}
+
 LT_DEV double gather_static(const LtDev& D, const double* arr, const Stencil& s)
 {
     double v[4] = { __ldg(arr + s.nd.x), __ldg(arr + s.nd.y), __ldg(arr + s.nd.z), __ldg(arr + s.nd.w) };

@@ -129,12 +129,9 @@ LT_WCTS_ATTR void wcts2(const LtDev& D, const T* const* fld, const Stencil* cons
     double vb[NF][4], vc[NF][4], vf[NF][4];
     Knots4 kb, kc, kf;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int k = deplvl - 1 + i;
-        zlev3<W>(D, col, k, kb.x[i], kc.x[i], kf.x[i]);
+    for (int f = 0; f < NF; ++f) gather4_bcf<T, PH>(D, fld[f], L, deplvl - 1, *st[f], grid[f], und, vb[f], vc[f], vf[f]);
 #pragma unroll
-        for (int f = 0; f < NF; ++f) gather_bcf<T, PH>(D, fld[f], L, k, *st[f], grid[f], und, vb[f][i], vc[f][i], vf[f][i]);
-    }
+    for (int i = 0; i < 4; ++i) zlev3<W>(D, col, deplvl - 1 + i, kb.x[i], kc.x[i], kf.x[i]);
     knots_prepare(kb); knots_prepare(kc);
     const bool first = D.p == 1;                     // (b,b,c): the forward profile is not used
     if (!first) knots_prepare(kf);
@@ -489,24 +486,33 @@ struct VtCtx {
     LT_DEV VtCtx(const LtDev& D_) : D(D_) {}
 
     LT_DEV double knot_x(int k) const { double x = fma((double)k - 0.5, H, Z1); x = k <= 1 ? Z1 : x; return k >= p2 ? ZN : x; }
-    LT_DEV double newx(int t, int j) const { return zl[t][0] + (double)(j - 4) * hs[t]; }
-    // piecewise-linear KH profile at newx(j): smallest jlo >= 1 with wz(jlo+1) > x (:135-166), pads (:169-177)
-    LT_DEV double newy(int t, int j, int& lev) const
+    double z1[3];
+    LT_DEV double newx(int t, int j) const { return z1[t] + (double)(j - 4) * hs[t]; }
+    // piecewise-linear KH profile at newx(j): smallest jlo >= 1 with wz(jlo+1) > x (:135-166), pads
+    // (:169-177).  The current segment lives in registers (slope, intercept, upper end); the
+    // thread-local profile arrays are only read when a pointer moves to the next level.
+    struct Seg { double slope, icpt, znext; int lev; };
+    LT_DEV void seg_load(Seg& g, int t, int lev) const
+    {   // lev = jlo (1-based)
+        double zlo = zl[t][lev - 1], zhi = zl[t][lev], klo = khp[t][lev - 1], khi = khp[t][lev];
+        g.lev = lev; g.slope = qdiv(klo - khi, zlo - zhi); g.icpt = klo - g.slope * zlo; g.znext = zhi;   // :126-133
+    }
+    LT_DEV double newy(int t, int j, Seg& g) const
     {
         if (j <= 4) return khp[0][0];                                  // ledger 11: KHb(1) for all three times
         if (j >= p2 + 4) return khp[t][ws - 1];
         double x = newx(t, j);
-        while (!(zl[t][lev] > x) && lev < ws - 1) ++lev;               // lev = jlo (1-based) -> zl[lev] is wz(jlo+1)
-        double zlo = zl[t][lev - 1], zhi = zl[t][lev], klo = khp[t][lev - 1], khi = khp[t][lev];
-        double slope = qdiv(klo - khi, zlo - zhi);                     // :126-133
-        return slope * x + (klo - slope * zlo);
+        while (!(g.znext > x) && g.lev < ws - 1) seg_load(g, t, g.lev + 1);
+        return g.slope * x + g.icpt;
     }
     // knot values, slopes and tension factors for knots [ka_, ka_ + VW - 1] /\ [1, p2]
     LT_DEVN void build(int ka_)
     {
         ka = ka_; kb = min(p2, ka + VW - 1);
         const int k0 = max(ka, 2), k1 = min(kb, p2 - 1);
-        double S[3] = {0.0, 0.0, 0.0}; int hi[3] = {1, 1, 1}, lo[3] = {1, 1, 1};
+        double S[3] = {0.0, 0.0, 0.0}; Seg hi[3], lo[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { seg_load(hi[t], t, 1); lo[t] = hi[t]; }
         if (k0 <= k1) {
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -605,7 +611,7 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     }
     const double rp2 = 1.0 / (double)V.p2;
 #pragma unroll
-    for (int t = 0; t < 3; ++t) V.hs[t] = (V.zl[t][V.ws - 1] - V.zl[t][0]) * rp2;
+    for (int t = 0; t < 3; ++t) { V.z1[t] = V.zl[t][0]; V.hs[t] = (V.zl[t][V.ws - 1] - V.zl[t][0]) * rp2; }
     V.Z1 = lag(D.LW4, V.zl[0][0], V.zl[1][0], V.zl[2][0]);
     V.ZN = lag(D.LW4, V.zl[0][V.ws - 1], V.zl[1][V.ws - 1], V.zl[2][V.ws - 1]);
     V.H = (V.ZN - V.Z1) * rp2; V.rH = qrcp(V.H);
