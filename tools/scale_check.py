@@ -1,0 +1,33 @@
+"""Gulf-scale shape check (BASELINE configs[3]/[4] per-GPU share): 1024x768 rho grid, us 36 /
+ws 37, 12.5 M buoyant particles (Behavior 6, sink > 0), HTurb + VTurb, open boundary, one GPU.
+Not a bench line: it verifies that the per-GPU shard of the 100 M-particle configuration fits
+and runs, and prints its device time and memory."""
+import sys, os, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from common import World, LtransLib, make_params
+import torch
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 12_500_000
+t0 = time.time()
+w = World(ni=1024, nj=768, us=36, hmin=50.0, hmax=3000.0, dlon=0.02, dlat=0.018, speed=0.9)
+prm = make_params(w, n, Behavior=6, sink=0.002, settlementon=0, mortality=0, TrackCollisions=0, ErrorFlag=3)
+g = LtransLib().create(prm)
+g.set_grid(w.grid()); g.set_bounds(w.bounds())
+x, y, z, dob, r, u, v = w.seed_particles(n)
+g.set_particles(x, y, z, dob, None, r, u, v)
+recs = [w.record(k) for k in range(4)]
+for k in range(3):
+    g.push_hydro(recs[k])
+g.sync()
+print("setup %.1f s, device memory used %.2f GB" % (time.time() - t0, (torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9), flush=True)
+stepIT = prm.dt // prm.idt
+g.run_external(1); g.sync()
+g.timer_start(); g.run_external(2); ms = g.timer_stop()
+print("external step 2: %.1f ms -> %.3e particle-steps/s" % (ms, n * stepIT / (ms * 1e-3)))
+g.push_hydro(recs[3]); g.rotate_hydro()
+g.kernel_times(True); g.run_external(3); km, ks = g.kernel_times(False)
+print("kernels ms per internal step:", [round(v / ks, 2) for v in km[:3]])
+st = g.stats(); f = g.fetch(("z", "status"))
+print("stats", st.tolist(), "finite", bool(np.isfinite(f["z"]).all()), "events", g.drain_events(5)[:5])
