@@ -361,22 +361,31 @@ LT_DEV void particle_error(const LtDev& D, int n, int code, double revertZ)
 
 
 // ============================================================ kernel 1: advect ==
+// State carried through the advect kernel.  The kernel body is prologue -> 4 x stage ->
+// epilogue with a block barrier before every stage: particles that drop out at a gate keep
+// reaching the barriers, and the warps of a block enter each RK stage together, so they fetch
+// the same instructions (instruction fetch was k_advect's top stall).
+struct AdvS {
+    Stage2 st; ColK col;
+    double Xpar, Ypar, Zpar, P_zb, P_zc, P_zf, P_depth, P_angle, ca, sa, minpd, maxpd, sU, sV, sW, xs, ys, zs;
+};
+
 template <class T, int PH>
-LT_DEV void advect_particle(const LtDev& D, int n)
+LT_DEV bool advect_prologue(const LtDev& D, int n, AdvS& S)
 {
     const ltgpu_params& P = D.P;
     const int idt = P.idt;
     D.s_act[n] = 0;
-    if (D.ix[2] <= D.dob[n]) return;                                     // :790-795
+    if (D.ix[2] <= D.dob[n]) return false;                               // :790-795
     double age = D.age[n] + (double)(float)idt;                          // :798
     D.age[n] = age;
     uint8_t fl = D.flags[n];
     if (age >= P.deadage && P.mortality) {                               // updateStatus behavior:162-179
         if (!(P.settlementon && (fl & LT_F_SETTLED))) { fl |= LT_F_DEAD; D.flags[n] = fl; }
     }
-    if (P.settlementon && (fl & LT_F_SETTLED)) return;                   // :804-816
-    if (P.mortality && (fl & LT_F_DEAD)) return;
-    if (P.OpenOceanBoundary && (fl & LT_F_OOB)) return;
+    if (P.settlementon && (fl & LT_F_SETTLED)) return false;             // :804-816
+    if (P.mortality && (fl & LT_F_DEAD)) return false;
+    if (P.OpenOceanBoundary && (fl & LT_F_OOB)) return false;
 
     const double Xpar = D.x[n], Ypar = D.y[n], Zold = D.z[n];
     int re = D.r_ele[n], ue = D.u_ele[n], ve = D.v_ele[n];
@@ -390,12 +399,11 @@ LT_DEV void advect_particle(const LtDev& D, int n)
         if (ve != ve0) D.v_ele[n] = ve;
         if (err) {
             particle_error(D, n, err == 4 ? LTGPU_EV_NOT_IN_RHO : err == 5 ? LTGPU_EV_NOT_IN_U : LTGPU_EV_NOT_IN_V, Zold);
-            return;
+            return false;
         }
     }
-    Stage2 st;
-    load_stencils(D, re, ue, ve, st);
-    Stencil s0 = st.r; s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights(st.r.q, Xpar, Ypar, true);    // setInterp :882
+    load_stencils(D, re, ue, ve, S.st);
+    Stencil s0 = S.st.r; s0.xp = Xpar; s0.yp = Ypar; s0.w = make_weights(S.st.r.q, Xpar, Ypar, true);    // setInterp :882
     const double P_depth = -1.0 * gather_static(D, D.depth, s0);         // :892-896
     const double P_angle = gather_static(D, D.angle, s0);
     double P_zetab, P_zetac, P_zetaf;
@@ -407,43 +415,54 @@ LT_DEV void advect_particle(const LtDev& D, int n)
     if (Zp > P_zetac) P_zc = P_zetac - (double)kF32_1em3;
     if (Zp > P_zetaf) P_zf = P_zetaf - (double)kF32_1em3;
     const double Zpar = lag(D.LWz, P_zb, P_zc, P_zf);                    // :914 (raw b,c,f triplet: ledger 8)
-    ColK col; col.zb = P_zetab; col.zc = P_zetac; col.zf = P_zetaf; col.depth = P_depth; col.h = -1.0 * P_depth;
-
-    const int ws = P.ws;
+    ColK& col = S.col; col.zb = P_zetab; col.zc = P_zetac; col.zf = P_zetaf; col.depth = P_depth; col.h = -1.0 * P_depth;
     double a, b, c;
-    zlev3<true>(D, col, 0, a, b, c);      const double maxpartdepth = fmax(a, fmax(b, c));    // :981-987
-    zlev3<true>(D, col, ws - 1, a, b, c); const double minpartdepth = fmin(a, fmin(b, c));
-    const double ca = cos(P_angle), sa = sin(P_angle);
+    zlev3<true>(D, col, 0, a, b, c);        S.maxpd = fmax(a, fmax(b, c));                      // :981-987
+    zlev3<true>(D, col, P.ws - 1, a, b, c); S.minpd = fmin(a, fmin(b, c));
+    S.ca = cos(P_angle); S.sa = sin(P_angle);
+    S.Xpar = Xpar; S.Ypar = Ypar; S.Zpar = Zpar; S.P_zb = P_zb; S.P_zc = P_zc; S.P_zf = P_zf;
+    S.P_depth = P_depth; S.P_angle = P_angle;
+    S.sU = 0.0; S.sV = 0.0; S.sW = 0.0; S.xs = Xpar; S.ys = Ypar; S.zs = Zpar;
+    return true;
+}
+
+// one RK stage; stage times are (t-h, t, t, t+h) = versions 1,2,2,3 (ledger 6)
+template <class T, int PH>
+LT_DEV void advect_stage(const LtDev& D, AdvS& S, int stg)
+{
     const double eps6 = (double)kF32_1em6;
-    double sU = 0.0, sV = 0.0, sW = 0.0, xs = Xpar, ys = Ypar, zs = Zpar;
-    // RK4 with stage times (t-h, t, t, t+h) = versions 1,2,2,3 (ledger 6)
-#pragma unroll 1
-    for (int stg = 0; stg < 4; ++stg) {
-        double Uad, Vad, Wad;
-        stage_weights2(st, xs, ys);
-        find_currents2<T, PH>(D, st, col, zs, P_zb, P_zc, P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad);
-        double wgt = (stg == 0 || stg == 3) ? 1.0 : 2.0;
-        sU += wgt * Uad; sV += wgt * Vad; sW += wgt * Wad;
-        if (stg < 3) {
-            double f = (double)idt;
-            if (stg < 2) {
-                xs = Xpar + (Uad * ca - Vad * sa) * f / 2.0; ys = Ypar + (Uad * sa + Vad * ca) * f / 2.0; zs = Zpar + Wad * f / 2.0;
-            } else {
-                xs = Xpar + (Uad * ca - Vad * sa) * f; ys = Ypar + (Uad * sa + Vad * ca) * f; zs = Zpar + Wad * f;
-            }
-            if (zs > minpartdepth) zs = minpartdepth - eps6;
-            if (zs < maxpartdepth) zs = maxpartdepth + eps6;
+    double Uad, Vad, Wad;
+    stage_weights2(S.st, S.xs, S.ys);
+    find_currents2<T, PH>(D, S.st, S.col, S.zs, S.P_zb, S.P_zc, S.P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad);
+    const double wgt = (stg == 0 || stg == 3) ? 1.0 : 2.0;
+    S.sU += wgt * Uad; S.sV += wgt * Vad; S.sW += wgt * Wad;
+    if (stg < 3) {
+        const double f = (double)D.P.idt, ca = S.ca, sa = S.sa;
+        if (stg < 2) {
+            S.xs = S.Xpar + (Uad * ca - Vad * sa) * f / 2.0; S.ys = S.Ypar + (Uad * sa + Vad * ca) * f / 2.0; S.zs = S.Zpar + Wad * f / 2.0;
+        } else {
+            S.xs = S.Xpar + (Uad * ca - Vad * sa) * f; S.ys = S.Ypar + (Uad * sa + Vad * ca) * f; S.zs = S.Zpar + Wad * f;
         }
+        if (S.zs > S.minpd) S.zs = S.minpd - eps6;
+        if (S.zs < S.maxpd) S.zs = S.maxpd + eps6;
     }
-    const double P_U = sU / 6.0, P_V = sV / 6.0, P_W = sW / 6.0;         // :1047-1049
+}
+
+template <class T, int PH>
+LT_DEV void advect_epilogue(const LtDev& D, int n, AdvS& S)
+{
+    const ltgpu_params& P = D.P;
+    const int idt = P.idt;
+    const double Xpar = S.Xpar, Ypar = S.Ypar, ca = S.ca, sa = S.sa;
+    const double P_U = S.sU / 6.0, P_V = S.sV / 6.0, P_W = S.sW / 6.0;   // :1047-1049
     double newX = Xpar + idt * (P_U * ca - P_V * sa);                    // :1051-1053, :1128-1130
     double newY = Ypar + idt * (P_U * sa + P_V * ca);
     if (P.SaltTempOn) {                                                  // :1062-1076
-        stage_weights2(st, Xpar, Ypar);
-        int deplvl = level_window2<false>(D, col, Zpar, P.us);
-        const T* f2[2] = {(const T*)D.salt, (const T*)D.temp}; const Stencil* s2[2] = {&st.r, &st.r}; const int g2[2] = {G_RHO, G_RHO};
+        stage_weights2(S.st, Xpar, Ypar);
+        int deplvl = level_window2<false>(D, S.col, S.Zpar, P.us);
+        const T* f2[2] = {(const T*)D.salt, (const T*)D.temp}; const Stencil* s2[2] = {&S.st.r, &S.st.r}; const int g2[2] = {G_RHO, G_RHO};
         double o[2];
-        wcts2<T, PH, false, 2>(D, f2, s2, g2, st.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o);
+        wcts2<T, PH, false, 2>(D, f2, s2, g2, S.st.u.nd, P.us, S.col, deplvl, S.P_zb, S.P_zc, S.P_zf, 3, o);
         D.psalt[n] = o[0]; D.ptemp[n] = o[1];
     }
     if (P.HTurbOn) {                                                     // hor_turb_module.f90:29-50
@@ -453,9 +472,9 @@ LT_DEV void advect_particle(const LtDev& D, int n)
         newX = (Xpar + idt * (P_U * ca - P_V * sa)) + box_muller_n(D, r.x, r.y) * sd;
         newY = (Ypar + idt * (P_U * sa + P_V * ca)) + box_muller_n(D, r.z, r.w) * sd;
     }
-    D.s_depth[n] = P_depth; D.s_angle[n] = P_angle;
-    D.s_zeb[n] = P_zetab; D.s_zec[n] = P_zetac; D.s_zef[n] = P_zetaf;
-    D.s_pzb[n] = P_zb; D.s_pzc[n] = P_zc; D.s_pzf[n] = P_zf; D.s_zpar[n] = Zpar;
+    D.s_depth[n] = S.P_depth; D.s_angle[n] = S.P_angle;
+    D.s_zeb[n] = S.col.zb; D.s_zec[n] = S.col.zc; D.s_zef[n] = S.col.zf;
+    D.s_pzb[n] = S.P_zb; D.s_pzc[n] = S.P_zc; D.s_pzf[n] = S.P_zf; D.s_zpar[n] = S.Zpar;
     D.s_nx[n] = newX; D.s_ny[n] = newY; D.s_advz[n] = idt * P_W;
     D.s_pu[n] = P_U; D.s_pv[n] = P_V; D.s_turbv[n] = 0.0;
     D.s_act[n] = 1;

@@ -17,29 +17,51 @@
 #include <cub/device/device_radix_sort.cuh>
 
 // ------------------------------------------------------------------ kernels --
-#ifndef LT_LB_ADV
-#define LT_LB_ADV 4
+// Block shapes (threads, min resident blocks) per kernel, from the sweep in profiles/r01_notes.md:
+// large blocks keep the warps of a block in step (same code region -> fewer instruction-fetch
+// stalls) and, after the cell re-sort, on neighbouring particles.
+#ifndef LT_BLK_ADV
+#define LT_BLK_ADV 512
 #endif
-#ifndef LT_LB_VT
-#define LT_LB_VT 6
+#ifndef LT_MIN_ADV
+#define LT_MIN_ADV 1
 #endif
-#ifndef LT_LB_FIN
-#define LT_LB_FIN 4
+#ifndef LT_BLK_VT
+#define LT_BLK_VT 384
+#endif
+#ifndef LT_MIN_VT
+#define LT_MIN_VT 2
+#endif
+#ifndef LT_BLK_FIN
+#define LT_BLK_FIN 128
+#endif
+#ifndef LT_MIN_FIN
+#define LT_MIN_FIN 4
 #endif
 template <class T, int PH>
-__global__ void __launch_bounds__(128, LT_LB_ADV) k_advect(const __grid_constant__ LtDev D)
+__global__ void __launch_bounds__(LT_BLK_ADV, LT_MIN_ADV) k_advect(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n < D.n) advect_particle<T, PH>(D, n);
+    AdvS S;
+    bool act = n < D.n;
+    if (act) act = advect_prologue<T, PH>(D, n, S);
+#pragma unroll 1
+    for (int stg = 0; stg < 4; ++stg) {
+#ifndef LT_NO_STAGE_BARRIER
+        __syncthreads();
+#endif
+        if (act) advect_stage<T, PH>(D, S, stg);
+    }
+    if (act) advect_epilogue<T, PH>(D, n, S);
 }
 template <class T, int PH>
-__global__ void __launch_bounds__(128, LT_LB_VT) k_vturb(const __grid_constant__ LtDev D)
+__global__ void __launch_bounds__(LT_BLK_VT, LT_MIN_VT) k_vturb(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < D.n) vturb_particle<T, PH>(D, n);
 }
 template <class T, int PH>
-__global__ void __launch_bounds__(128, LT_LB_FIN) k_finish(const __grid_constant__ LtDev D)
+__global__ void __launch_bounds__(LT_BLK_FIN, LT_MIN_FIN) k_finish(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < D.n) finish_particle<T, PH>(D, n);
@@ -746,13 +768,12 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
         for (int t = 0; t < 3; ++t) D.LW4[t] = (D.LW[0][t] + 4.0 * D.LW[1][t] + D.LW[2][t]) / 6.0;
     }
     {
-        int blocks = (D.n + 127) / 128;
         const bool vt = ctx->prm.VTurbOn != 0;
         cudaStream_t st = ctx->compute;
 #define LT_LAUNCH(T, PH) do { if (ctx->timing) cudaEventRecord(ctx->tev[0], st); \
-                              k_advect<T, PH><<<blocks, 128, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[1], st); \
-                              if (vt) k_vturb<T, PH><<<blocks, 128, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[2], st); \
-                              k_finish<T, PH><<<blocks, 128, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[3], st); } while (0)
+                              k_advect<T, PH><<<(D.n + LT_BLK_ADV - 1) / LT_BLK_ADV, LT_BLK_ADV, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[1], st); \
+                              if (vt) k_vturb<T, PH><<<(D.n + LT_BLK_VT - 1) / LT_BLK_VT, LT_BLK_VT, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[2], st); \
+                              k_finish<T, PH><<<(D.n + LT_BLK_FIN - 1) / LT_BLK_FIN, LT_BLK_FIN, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[3], st); } while (0)
 #define LT_LAUNCH_T(T) do { switch (D.sb) { case 0: LT_LAUNCH(T, 0); break; case 1: LT_LAUNCH(T, 1); break; \
                                             case 2: LT_LAUNCH(T, 2); break; default: LT_LAUNCH(T, 3); break; } } while (0)
         if (ctx->esz == 4) LT_LAUNCH_T(float); else LT_LAUNCH_T(double);
