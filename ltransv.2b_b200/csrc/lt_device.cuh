@@ -81,6 +81,15 @@ template <int PH> LT_DEV void pick3(double a0, double a1, double a2, double a3, 
 }
 template <class T, int PH> struct LoadBCF;
 template <int PH> struct LoadBCF<float, PH> {
+    typedef float4 Raw;
+    static LT_DEV Raw load(const float* base, size_t idx) { return __ldg(reinterpret_cast<const float4*>(base) + idx); }
+    static LT_DEV void pick(const Raw& q, double& b, double& c, double& f)
+    {
+        float fb, fc, ff;
+        if (PH == 0) { fb = q.x; fc = q.y; ff = q.z; } else if (PH == 1) { fb = q.y; fc = q.z; ff = q.w; }
+        else if (PH == 2) { fb = q.z; fc = q.w; ff = q.x; } else { fb = q.w; fc = q.x; ff = q.y; }
+        b = (double)fb; c = (double)fc; f = (double)ff;
+    }
     static LT_DEV void get(const float* base, size_t idx, double& b, double& c, double& f)
     {
         float4 q = __ldg(reinterpret_cast<const float4*>(base) + idx);
@@ -91,6 +100,13 @@ template <int PH> struct LoadBCF<float, PH> {
     }
 };
 template <int PH> struct LoadBCF<double, PH> {
+    struct Raw { double2 lo, hi; };
+    static LT_DEV Raw load(const double* base, size_t idx)
+    {
+        const double2* p = reinterpret_cast<const double2*>(base) + 2 * idx;
+        Raw r; r.lo = __ldg(p); r.hi = __ldg(p + 1); return r;
+    }
+    static LT_DEV void pick(const Raw& q, double& b, double& c, double& f) { pick3<PH>(q.lo.x, q.lo.y, q.hi.x, q.hi.y, b, c, f); }
     static LT_DEV void get(const double* base, size_t idx, double& b, double& c, double& f)
     {
         const double2* p = reinterpret_cast<const double2*>(base) + 2 * idx;
@@ -285,21 +301,25 @@ template <class T, int PH>
 LT_DEVN void gather4_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
                          double* __restrict__ vb, double* __restrict__ vc, double* __restrict__ vf)
 {
-    double b[4][4], c[4][4], f[4][4];           // [level][corner]
+    // all 16 vector loads are issued first and held RAW (float4: 64 registers for f32; the
+    // converted doubles would need 96 and spill), then converted and combined level by level
+    typedef typename LoadBCF<T, PH>::Raw Raw;
     const size_t n0 = (size_t)s.nd.x * L + lev0, n1 = (size_t)s.nd.y * L + lev0, n2 = (size_t)s.nd.z * L + lev0, n3 = (size_t)s.nd.w * L + lev0;
+    Raw r[4][4];                                 // [level][corner]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        LoadBCF<T, PH>::get(fld, n0 + i, b[i][0], c[i][0], f[i][0]);
-        LoadBCF<T, PH>::get(fld, n1 + i, b[i][1], c[i][1], f[i][1]);
-        LoadBCF<T, PH>::get(fld, n2 + i, b[i][2], c[i][2], f[i][2]);
-        LoadBCF<T, PH>::get(fld, n3 + i, b[i][3], c[i][3], f[i][3]);
+        r[i][0] = LoadBCF<T, PH>::load(fld, n0 + i); r[i][1] = LoadBCF<T, PH>::load(fld, n1 + i);
+        r[i][2] = LoadBCF<T, PH>::load(fld, n2 + i); r[i][3] = LoadBCF<T, PH>::load(fld, n3 + i);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if (D.P.FreeSlip) gather_freeslip(D, b[i], c[i], f[i], s.nd, grid, und);
-        vb[i] = combine(s.w, b[i][0], b[i][1], b[i][2], b[i][3]);
-        vc[i] = combine(s.w, c[i][0], c[i][1], c[i][2], c[i][3]);
-        vf[i] = combine(s.w, f[i][0], f[i][1], f[i][2], f[i][3]);
+        double b[4], c[4], f[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) LoadBCF<T, PH>::pick(r[i][q], b[q], c[q], f[q]);
+        if (D.P.FreeSlip) gather_freeslip(D, b, c, f, s.nd, grid, und);
+        vb[i] = combine(s.w, b[0], b[1], b[2], b[3]);
+        vc[i] = combine(s.w, c[0], c[1], c[2], c[3]);
+        vf[i] = combine(s.w, f[0], f[1], f[2], f[3]);
     }
 }
 
