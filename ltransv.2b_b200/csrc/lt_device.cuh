@@ -272,19 +272,28 @@ LT_DEVN void gather_freeslip(const LtDev& D, double* b, double* c, double* f, in
 // getInterp (hydro:1743-2005) / interp (hydro:2008-2569) with precomputed weights.
 // Out of line on purpose: ~16 call sites per kernel; inlined they made k_advect 15 k SASS
 // instructions and instruction fetch its top stall (profiles/r01_notes.md).
+// FreeSlip works on COPIES: taking the address of b/c/f for the (normally dead) call would
+// force the twelve values of every gather into local memory.
+#define LT_FREESLIP4(b0, b1, b2, b3, c0, c1, c2, c3, f0, f1, f2, f3) do { if (D.P.FreeSlip) { \
+        double bb_[4] = {b0, b1, b2, b3}, cc_[4] = {c0, c1, c2, c3}, ff_[4] = {f0, f1, f2, f3}; \
+        gather_freeslip(D, bb_, cc_, ff_, s.nd, grid, und); \
+        b0 = bb_[0]; b1 = bb_[1]; b2 = bb_[2]; b3 = bb_[3]; c0 = cc_[0]; c1 = cc_[1]; c2 = cc_[2]; c3 = cc_[3]; \
+        f0 = ff_[0]; f1 = ff_[1]; f2 = ff_[2]; f3 = ff_[3]; } } while (0)
+
 template <class T, int PH>
 LT_DEV void gather_bcf_inl(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
                            double& rb, double& rc, double& rf)
 {
-    double b[4], c[4], f[4];
-    LoadBCF<T, PH>::get(fld, (size_t)s.nd.x * L + lev0, b[0], c[0], f[0]);
-    LoadBCF<T, PH>::get(fld, (size_t)s.nd.y * L + lev0, b[1], c[1], f[1]);
-    LoadBCF<T, PH>::get(fld, (size_t)s.nd.z * L + lev0, b[2], c[2], f[2]);
-    LoadBCF<T, PH>::get(fld, (size_t)s.nd.w * L + lev0, b[3], c[3], f[3]);
-    if (D.P.FreeSlip) gather_freeslip(D, b, c, f, s.nd, grid, und);
-    rb = combine(s.w, b[0], b[1], b[2], b[3]);
-    rc = combine(s.w, c[0], c[1], c[2], c[3]);
-    rf = combine(s.w, f[0], f[1], f[2], f[3]);
+    const Wt w = s.w;
+    double b0, b1, b2, b3, c0, c1, c2, c3, f0, f1, f2, f3;
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.x * L + lev0, b0, c0, f0);
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.y * L + lev0, b1, c1, f1);
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.z * L + lev0, b2, c2, f2);
+    LoadBCF<T, PH>::get(fld, (size_t)s.nd.w * L + lev0, b3, c3, f3);
+    LT_FREESLIP4(b0, b1, b2, b3, c0, c1, c2, c3, f0, f1, f2, f3);
+    rb = combine(w, b0, b1, b2, b3);
+    rc = combine(w, c0, c1, c2, c3);
+    rf = combine(w, f0, f1, f2, f3);
 }
 template <class T, int PH>
 LT_DEVN void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
@@ -311,15 +320,16 @@ LT_DEVN void gather4_bcf(const LtDev& D, const T* fld, int L, int lev0, const St
         r[i][0] = LoadBCF<T, PH>::load(fld, n0 + i); r[i][1] = LoadBCF<T, PH>::load(fld, n1 + i);
         r[i][2] = LoadBCF<T, PH>::load(fld, n2 + i); r[i][3] = LoadBCF<T, PH>::load(fld, n3 + i);
     }
+    const Wt w = s.w;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        double b[4], c[4], f[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) LoadBCF<T, PH>::pick(r[i][q], b[q], c[q], f[q]);
-        if (D.P.FreeSlip) gather_freeslip(D, b, c, f, s.nd, grid, und);
-        vb[i] = combine(s.w, b[0], b[1], b[2], b[3]);
-        vc[i] = combine(s.w, c[0], c[1], c[2], c[3]);
-        vf[i] = combine(s.w, f[0], f[1], f[2], f[3]);
+        double b0, b1, b2, b3, c0, c1, c2, c3, f0, f1, f2, f3;
+        LoadBCF<T, PH>::pick(r[i][0], b0, c0, f0); LoadBCF<T, PH>::pick(r[i][1], b1, c1, f1);
+        LoadBCF<T, PH>::pick(r[i][2], b2, c2, f2); LoadBCF<T, PH>::pick(r[i][3], b3, c3, f3);
+        LT_FREESLIP4(b0, b1, b2, b3, c0, c1, c2, c3, f0, f1, f2, f3);
+        vb[i] = combine(w, b0, b1, b2, b3);
+        vc[i] = combine(w, c0, c1, c2, c3);
+        vf[i] = combine(w, f0, f1, f2, f3);
     }
 }
 
