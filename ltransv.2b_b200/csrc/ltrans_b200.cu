@@ -204,6 +204,9 @@ struct ltgpu_ctx {
     unsigned *d_key = nullptr, *d_key2 = nullptr; int *d_idx = nullptr, *d_perm = nullptr, *d_pid = nullptr;
     void* d_cub = nullptr; size_t cub_bytes = 0;
     double* spare8 = nullptr; int* spare4 = nullptr; uint8_t* spare1 = nullptr; double* out8 = nullptr;
+    void* h_out[2] = {nullptr, nullptr};     // pinned bounce buffers for fetch (pageable D2H is 4-5x slower)
+    cudaEvent_t out_done[2] = {nullptr, nullptr}; int out_i = 0;
+    void* pend_host[2] = {nullptr, nullptr}; size_t pend_bytes[2] = {0, 0};
     int key_bits = 32;
     long long sorts = 0;
     // optional per-kernel timing (ltgpu_kernel_times)
@@ -402,17 +405,38 @@ static int32_t resort(ltgpu_ctx* ctx)
     ctx->sorts++;
     return LTGPU_OK;
 }
-// copy one per-slot column to the host in particle order
+// copy one per-slot column to the host in particle order: scatter on the device, D2H into a
+// pinned bounce buffer (double buffered so the next column's copy overlaps this memcpy)
 template <class V>
 static int32_t fetch_col(ltgpu_ctx* ctx, V* host, const V* dev)
 {
     if (!host) return LTGPU_OK;
     int n = ctx->D.n;
-    V* tmp = (V*)ctx->out8;
+    size_t bytes = sizeof(V) * (size_t)n;
+    int b = ctx->out_i; ctx->out_i ^= 1;
+    V* tmp = (V*)(b ? (void*)ctx->spare8 : (void*)ctx->out8);       // spare8 is free between re-sorts
     k_scatter<V><<<(n + 255) / 256, 256, 0, ctx->compute>>>(dev, tmp, ctx->d_pid, n);
     ctx->launches++;
-    CK(cudaMemcpyAsync(host, tmp, sizeof(V) * (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
-    CK(cudaStreamSynchronize(ctx->compute));
+    CK(cudaMemcpyAsync(ctx->h_out[b], tmp, bytes, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaEventRecord(ctx->out_done[b], ctx->compute));
+    ctx->pend_host[b] = host; ctx->pend_bytes[b] = bytes;
+    // finish the PREVIOUS column while this one is in flight
+    int pb = b ^ 1;
+    if (ctx->pend_host[pb]) {
+        CK(cudaEventSynchronize(ctx->out_done[pb]));
+        memcpy(ctx->pend_host[pb], ctx->h_out[pb], ctx->pend_bytes[pb]);
+        ctx->pend_host[pb] = nullptr;
+    }
+    return LTGPU_OK;
+}
+static int32_t fetch_flush(ltgpu_ctx* ctx)
+{
+    for (int b = 0; b < 2; ++b)
+        if (ctx->pend_host[b]) {
+            CK(cudaEventSynchronize(ctx->out_done[b]));
+            memcpy(ctx->pend_host[b], ctx->h_out[b], ctx->pend_bytes[b]);
+            ctx->pend_host[b] = nullptr;
+        }
     return LTGPU_OK;
 }
 
@@ -463,6 +487,7 @@ int32_t ltgpu_destroy(ltgpu_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : ctx->owned) cudaFree(p);
+    for (int i = 0; i < 2; ++i) { if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]); if (ctx->out_done[i]) cudaEventDestroy(ctx->out_done[i]); }
     for (int i = 0; i < 2; ++i) { if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]); if (ctx->stage_done[i]) cudaEventDestroy(ctx->stage_done[i]); }
     for (int i = 0; i < 4; ++i) if (ctx->slot_ready[i]) cudaEventDestroy(ctx->slot_ready[i]);
     if (ctx->slot_free) cudaEventDestroy(ctx->slot_free);
@@ -666,6 +691,10 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
     TRY(dalloc(ctx, &ctx->d_pid, N)); TRY(dalloc(ctx, &ctx->d_perm, N)); TRY(dalloc(ctx, &ctx->d_idx, N));
     TRY(dalloc(ctx, &ctx->d_key, N)); TRY(dalloc(ctx, &ctx->d_key2, N));
     TRY(dalloc(ctx, &ctx->spare8, N)); TRY(dalloc(ctx, &ctx->spare4, N)); TRY(dalloc(ctx, &ctx->spare1, N)); TRY(dalloc(ctx, &ctx->out8, N));
+    for (int b = 0; b < 2; ++b) {          // pinned bounce buffers of ltgpu_fetch (allocated here: cudaMallocHost is slow)
+        CK(cudaMallocHost(&ctx->h_out[b], sizeof(double) * N));
+        CK(cudaEventCreateWithFlags(&ctx->out_done[b], cudaEventDisableTiming));
+    }
     k_iota<<<(n + 255) / 256, 256, 0, ctx->compute>>>(ctx->d_pid, n);
     D.pid = ctx->d_pid;
     {
@@ -826,7 +855,7 @@ int32_t ltgpu_fetch(ltgpu_ctx* ctx, double* x, double* y, double* z, double* age
     TRY(fetch_col(ctx, endpoly, (const int*)D.endpoly)); TRY(fetch_col(ctx, lifespan, (const double*)D.lifespan));
     TRY(fetch_col(ctx, r_ele, (const int*)D.r_ele)); TRY(fetch_col(ctx, u_ele, (const int*)D.u_ele)); TRY(fetch_col(ctx, v_ele, (const int*)D.v_ele));
     (void)N; (void)s;
-    return LTGPU_OK;
+    return fetch_flush(ctx);
 }
 
 int32_t ltgpu_reset_hits(ltgpu_ctx* ctx)
