@@ -204,7 +204,9 @@ def main():
         one_step(False)
     barrier()
     stop, samples = threading.Event(), []
-    th = threading.Thread(target=clocks_sampler, args=(stop, samples, local)); th.start()
+    # only rank 0 polls nvidia-smi (its own GPU): polling perturbs the polled GPU, and at N > 1 the
+    # first query of the other ranks slowed their first two timed steps by 20 %
+    th = threading.Thread(target=clocks_sampler if rank == 0 else (lambda *a: None), args=(stop, samples, local)); th.start()
     # ---- device-timed arm ---------------------------------------------------------
     launches0 = g.launch_count()
     dev_ms = 0.0

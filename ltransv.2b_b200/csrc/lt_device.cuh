@@ -403,6 +403,15 @@ LT_DEV double sig_guess(double T)
 // One Newton iteration of the convexity equation  SIG * T1(SIG) = TP1  (tension:528-579).
 // Returns true when the loop of the reference would exit; `out` is then the tension factor
 // (0 with err = 1 when the reference would raise SigErr).  State: SIG, NIT, chk, chk_at.
+#ifdef LT_DEBUG_TRACE
+__device__ unsigned long long g_dbgcnt[8];          // debug builds only: solver-cap census
+__device__ double g_dbgcase[8];                      // inputs of the last secant-cap case
+#define LT_DBG_COUNT(k) atomicAdd(&g_dbgcnt[k], 1ull)
+#define LT_DBG_MAX(k, v) atomicMax(&g_dbgcnt[k], (unsigned long long)(v))
+#else
+#define LT_DBG_COUNT(k)
+#define LT_DBG_MAX(k, v)
+#endif
 struct NewtonState { double SIG, TP1, chk; int NIT, chk_at; };
 LT_DEV void newton_start(NewtonState& q, double TP1, double SIG0) { q.SIG = SIG0; q.TP1 = TP1; q.chk = SIG0; q.NIT = 0; q.chk_at = 1; }
 LT_DEV bool newton_step(NewtonState& q, double& out, int& err)
@@ -423,17 +432,17 @@ LT_DEV bool newton_step(NewtonState& q, double& out, int& err)
         FP = T1 + SIG * (2.0 * SIG * EMS * RM_ - T1 * T1 + 1.0);
     }
     double F = SIG * T1 - q.TP1;
-    if (++q.NIT > 10000) { err = 1; out = 0.0; return true; }         // tension:556-559
+    if (++q.NIT > 10000) { LT_DBG_COUNT(0); err = 1; out = 0.0; return true; }         // tension:556-559
     if (FP <= 0.0) { out = fmin(SIG, SBIG); return true; }
     double DSIG = -qdiv(F, FP);
-    if (fabs(DSIG) <= RTOL * SIG || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) { out = fmin(SIG, SBIG); return true; }
+    if (fabs(DSIG) <= RTOL * SIG || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) { LT_DBG_MAX(2, q.NIT); out = fmin(SIG, SBIG); return true; }
     SIG = SIG + DSIG;
     q.SIG = SIG;
     // Newton's map SIG -> SIG' is a pure function of SIG.  When F's rounding noise sits just
     // above RTOL the iteration falls into a short cycle and the reference spins until
     // NIT > 10000 and raises SigErr.  A repeated iterate proves the cycle, so Brent's
     // checkpointing reaches the same verdict without 10^4 iterations.
-    if (SIG == q.chk) { err = 1; out = 0.0; return true; }
+    if (SIG == q.chk) { LT_DBG_COUNT(1); LT_DBG_MAX(5, q.NIT); err = 1; out = 0.0; return true; }
     if (q.NIT == q.chk_at) { q.chk = SIG; q.chk_at <<= 1; }
     return false;
 }
@@ -470,9 +479,14 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
     double DSIG = SIG, DMAX = SIG, D1PD2 = D1 + D2, A = 0.0, E = 0.0;
     bool CONT = true;                                  // ledger 18
     int NIT = 0;
+    // The reference's loop has no iteration cap (tension:664-754).  In the SIG <= .5 branch
+    // A*(C2+C1) is not guarded, so SQRT can return NaN; once F is NaN and the exit test of
+    // that pass fails every later pass is NaN too and the reference spins forever.  That is
+    // reported as SigErr (linint fallback in WCTS_ITPI) at once; the 10^5-pass backstop the
+    // oracle shares reaches the same verdict ~50 ms later.
     for (;;) {
         DSIG = qdiv(-F * DSIG, F - F0);
-        if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { err = 1; sigma = 0.0; return true; } continue; }
+        if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { LT_DBG_COUNT(3); err = 1; sigma = 0.0; return true; } continue; }
         if (fabs(DSIG) < STOL / 2.0) DSIG = -copysign(STOL / 2.0, DMAX);
         SIG = SIG + DSIG;
         F0 = F;
@@ -497,9 +511,16 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
             if (CONT) E = SIG * SSINH - SCM - SCM;
         }
         if (CONT) F = qdiv(SGN * (E * S2 - C2) + sqrt(A * (C2 + C1)), E);
-        if (++NIT > 100000) { err = 1; sigma = 0.0; return true; }
+        if (++NIT > 100000) {
+            LT_DBG_COUNT(3);
+#ifdef LT_DEBUG_TRACE
+            g_dbgcase[0] = DX; g_dbgcase[1] = Y1; g_dbgcase[2] = Y2; g_dbgcase[3] = S1; g_dbgcase[4] = S2; g_dbgcase[5] = SIG; g_dbgcase[6] = DSIG; g_dbgcase[7] = F;
+#endif
+            err = 1; sigma = 0.0; return true;
+        }
         STOL = RTOL * SIG;
         if (fabs(DMAX) <= STOL || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
+        if (!(F == F)) { LT_DBG_COUNT(6); err = 1; sigma = 0.0; return true; }
         DMAX = DMAX + DSIG;
         if (F0 * F > 0.0 && fabs(F) >= fabs(F0)) { DSIG = DMAX; F0 = FNEG; continue; }
         if (F0 * F <= 0.0) {
@@ -508,6 +529,7 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
             if (fabs(DSIG) > fabs(T1) && fabs(F) < fabs(T2)) { DSIG = T1; F0 = T2; }
         }
     }
+    LT_DBG_MAX(4, NIT);
     sigma = fmin(SIG, SBIG);
     return true;
 }

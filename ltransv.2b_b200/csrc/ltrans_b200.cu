@@ -957,6 +957,16 @@ int32_t ltgpu_debug_trace(ltgpu_ctx* ctx, int64_t id, double* out, int32_t n)
     return 0;
 }
 #endif
+#ifdef LT_DEBUG_TRACE
+int32_t ltgpu_debug_counters(ltgpu_ctx* ctx, unsigned long long* out, int32_t reset)
+{   // debug builds only: [0] Newton cap, [1] Newton cycle, [2] max Newton NIT, [3] secant cap, [4] max secant NIT
+    cudaStreamSynchronize(ctx->compute);
+    cudaMemcpyFromSymbol(out, g_dbgcnt, sizeof(unsigned long long) * 8);
+    cudaMemcpyFromSymbol(out + 8, g_dbgcase, sizeof(double) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbgcnt, z, sizeof z); }
+    return 0;
+}
+#endif
 int32_t ltgpu_kernel_times(ltgpu_ctx* ctx, int32_t enable, float ms[4], int64_t* steps)
 {
     if (!ctx) return LTGPU_E_ARG;
