@@ -405,6 +405,8 @@ LT_DEV double sig_guess(double T)
 // (0 with err = 1 when the reference would raise SigErr).  State: SIG, NIT, chk, chk_at.
 #ifdef LT_DEBUG_TRACE
 __device__ unsigned long long g_dbgcnt[8];          // debug builds only: solver-cap census
+__device__ unsigned long long g_dbgcnt2[8];         // VTurb build census
+__device__ unsigned long long g_dbghist[64];        // VTurb walk: intervals above / below the first one
 __device__ double g_dbgcase[8];                      // inputs of the last secant-cap case
 #define LT_DBG_COUNT(k) atomicAdd(&g_dbgcnt[k], 1ull)
 #define LT_DBG_MAX(k, v) atomicMax(&g_dbgcnt[k], (unsigned long long)(v))

@@ -528,6 +528,9 @@ struct VtCtx {
     LT_DEVN void build(int ka_)
     {
         ka = ka_; kb = min(p2, ka + VW - 1);
+#ifdef LT_DEBUG_TRACE
+        atomicAdd(&g_dbgcnt2[0], 1ull);                  // builds
+#endif
         const int k0 = max(ka, 2), k1 = min(kb, p2 - 1);
         double S[3] = {0.0, 0.0, 0.0}; Seg hi[3], lo[3];
 #pragma unroll
@@ -587,8 +590,15 @@ struct VtCtx {
         // one Newton loop per lane over all its pending intervals (see wcts2)
         int cur = 0; NewtonState ns;
         if (np > 0) newton_start(ns, tp[0], sg[pend[0]]);
+#ifdef LT_DEBUG_TRACE
+        atomicAdd(&g_dbgcnt2[1], (unsigned long long)np);            // convexity solves
+        atomicAdd(&g_dbgcnt2[3], (unsigned long long)(ib - ia + 1)); // intervals classified
+#endif
         while (cur < np) {
             double o; int e = 0;
+#ifdef LT_DEBUG_TRACE
+            atomicAdd(&g_dbgcnt2[2], 1ull);              // Newton iterations
+#endif
             if (newton_step(ns, o, e)) {
                 sg[pend[cur]] = o; if (e) sigerr = true;
                 if (++cur < np) newton_start(ns, tp[cur], sg[pend[cur]]);
@@ -644,11 +654,17 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     // are only touched when the particle changes interval (long-scoreboard stalls on those
     // arrays were k_vturb's top stall)
     int cI = -1; double cX1 = 0, cX2 = 0, cY1 = 0, cY2 = 0, cP1 = 0, cP2 = 0, cSG = 0;
+#ifdef LT_DEBUG_TRACE
+    int dI0 = -1, dImin = 1 << 30, dImax = -1;
+#endif
     auto load_iv = [&](double zq) {
         if (cI >= 0 && zq >= cX1 && zq < cX2) return;                  // still inside [X(I), X(I+1)): INTRVL gives I
         int I = V.interval(zq); V.need(I);
         int q = I - V.ka;
         cI = I; cX1 = V.knot_x(I); cX2 = V.knot_x(I + 1);
+#ifdef LT_DEBUG_TRACE
+        if (dI0 < 0) dI0 = I; dImin = min(dImin, I); dImax = max(dImax, I);
+#endif
         cY1 = V.fy[q]; cY2 = V.fy[q + 1]; cP1 = V.yp[q]; cP2 = V.yp[q + 1]; cSG = V.sg[q];
     };
 #pragma unroll 1
@@ -676,6 +692,9 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
         if (D.first_id + D.pid[n] == D.dbg_id) { D.dbg[4 * i] = ParZc; D.dbg[4 * i + 1] = Kprimec; D.dbg[4 * i + 2] = KH3rdc; D.dbg[4 * i + 3] = DEV; }
 #endif
     }
+#ifdef LT_DEBUG_TRACE
+    if (dI0 >= 0) { atomicAdd(&g_dbghist[min(dImax - dI0, 31)], 1ull); atomicAdd(&g_dbghist[32 + min(dI0 - dImin, 31)], 1ull); }
+#endif
     D.s_turbv[n] = P_zc - ParZc;                                        // :342
 }
 

@@ -963,7 +963,9 @@ int32_t ltgpu_debug_counters(ltgpu_ctx* ctx, unsigned long long* out, int32_t re
     cudaStreamSynchronize(ctx->compute);
     cudaMemcpyFromSymbol(out, g_dbgcnt, sizeof(unsigned long long) * 8);
     cudaMemcpyFromSymbol(out + 8, g_dbgcase, sizeof(double) * 8);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbgcnt, z, sizeof z); }
+    cudaMemcpyFromSymbol(out + 16, g_dbgcnt2, sizeof(unsigned long long) * 8);
+    cudaMemcpyFromSymbol(out + 24, g_dbghist, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbgcnt, z, sizeof z); cudaMemcpyToSymbol(g_dbgcnt2, z, sizeof z); unsigned long long zz[64] = {0}; cudaMemcpyToSymbol(g_dbghist, zz, sizeof zz); }
     return 0;
 }
 #endif
