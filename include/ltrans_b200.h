@@ -35,6 +35,11 @@ extern "C" {
                                 /* STOP condition of LTRANS.f90:835-856 etc.   */
 
 /* ---- per-particle event codes (ErrorLog.txt formats, LTRANS.f90:761-775) */
+#define LTGPU_EV_INIT_OUT_MAIN   11  /* initially outside main bounds  (LTRANS.f90:377) */
+#define LTGPU_EV_INIT_IN_ISLAND  12  /* initially inside island bounds (:400)            */
+#define LTGPU_EV_INIT_NOT_IN_RHO 13  /* initially not in rho element   (:446)            */
+#define LTGPU_EV_INIT_NOT_IN_U   14  /*                                (:448)            */
+#define LTGPU_EV_INIT_NOT_IN_V   15  /*                                (:450)            */
 #define LTGPU_EV_NOT_IN_RHO     21  /* setEle err 4 at step start  (:870)      */
 #define LTGPU_EV_NOT_IN_U       22  /* setEle err 5                (:872)      */
 #define LTGPU_EV_NOT_IN_V       23  /* setEle err 6                (:874)      */
@@ -165,12 +170,24 @@ int32_t ltgpu_set_habitat(ltgpu_ctx* ctx,
  * plus the element ids found by setEle_all (hydrodynamic_module.f90:1536).
  *  first_id : global 1-based id of local particle 0 (multi-GPU slices; keys the
  *             Philox stream so results do not depend on the sharding).
- *  r_ele,u_ele,v_ele may be NULL: the library then locates every particle by a
- *  whole-grid scan on the device (setEle first=.TRUE., hydro:1436-1457). */
+ *  r_ele,u_ele,v_ele may be NULL: the library then locates every particle on the
+ *  device with the result of the whole-grid scan (setEle first=.TRUE.,
+ *  hydro:1436-1457; 0 = in no element), through a bucket index over the elements. */
 int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
     const double* x, const double* y, const double* z, const double* dob,
     const int32_t* startpoly,
     const int32_t* r_ele, const int32_t* u_ele, const int32_t* v_ele);
+
+/* The start-up screen of ini_LTRANS on the device (LTRANS.f90:356-452; replaces the
+ * serial mbounds / ibounds loop and the check after setEle_all): particles
+ * released outside the main boundary, inside an island or in no rho / u / v
+ * element get die (ErrorFlag 2) or setOut (ErrorFlag 1, 3) and one event
+ * LTGPU_EV_INIT_* with time 0; counts[0..4] = how many of each code 11..15.
+ * ErrorFlag outside 1..3: returns LTGPU_E_PARTICLE and the lowest offending id
+ * (the reference STOPs).  Unlike the reference, every unlocated particle is
+ * reported, not only the first (its setEle_all leaves the rest unset, hydro:1594).
+ * Call after set_bounds and set_particles; optional. */
+int32_t ltgpu_screen_initial(ltgpu_ctx* ctx, int64_t counts[5], int64_t* bad_particle);
 
 /* Queue the next hydro record (ROMS memory order: node fastest, then level;
  * exactly one NF90_GET_VAR record, hydro:1140-1364).  The library applies the

@@ -163,9 +163,52 @@ __global__ void k_locate(const LtDev D, LtGridTab G, int* __restrict__ ele)
     if (n >= D.n) return;
     double X = D.x[n], Y = D.y[n];
     int found = 0;
-    for (int e = 0; e < G.nE; ++e)
-        if (gridcell(G.ele + (size_t)e * 8, X, Y)) { found = e + 1; break; }
+    // an element that holds the point has the point inside its bounding box, so it is listed in
+    // the point's bucket; bucket lists ascend, so the first hit is the full scan's first hit
+    int cx = (int)floor((X - G.lx0) * G.lrcs), cy = (int)floor((Y - G.ly0) * G.lrcs);
+    if (cx >= 0 && cy >= 0 && cx < G.lnx && cy < G.lny) {
+        int c = cy * G.lnx + cx;
+        for (int q = __ldg(G.lptr + c); q < __ldg(G.lptr + c + 1); ++q) {
+            int e = __ldg(G.lidx + q);
+            if (gridcell(G.ele + (size_t)e * 8, X, Y)) { found = e + 1; break; }
+        }
+    }
     ele[n] = found;
+}
+
+// The start-up screen of ini_LTRANS (LTRANS.f90:356-452): particles released outside the main
+// boundary, inside an island, or in no rho / u / v element.  ErrorFlag 2 -> die, 1 or 3 -> setOut,
+// anything else is the reference's STOP (lowest id reported through d_bad).
+__global__ void k_screen(const LtDev D, unsigned long long* __restrict__ cnt)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= D.n) return;
+    double X = D.x[n], Y = D.y[n];
+    int code = 0;
+    {                                                                    // mbounds :362
+        int in = inpoly_banded(X, Y, D.bxy, D.mb_y0, D.mb_rbh, D.mb_n, D.mb_ptr, D.mb_idx);
+        if (in == 2) in = inpoly(X, Y, D.maxbound, D.bxy, false) ? 1 : 0;
+        if (!in) code = LTGPU_EV_INIT_OUT_MAIN;
+    }
+    if (!code && D.maxisland > 0) {                                      // ibounds :385
+        int in = D.ib_ok ? inpoly_banded(X, Y, D.hxy, D.ib_y0, D.ib_rbh, D.ib_n, D.ib_ptr, D.ib_idx) : 2;
+        if (in == 2) in = in_any_island(D, X, Y) ? 1 : 0;
+        if (in) code = LTGPU_EV_INIT_IN_ISLAND;
+    }
+    if (!code) {                                                         // setEle_all :412-452
+        if (D.r_ele[n] == 0) code = LTGPU_EV_INIT_NOT_IN_RHO;
+        else if (D.u_ele[n] == 0) code = LTGPU_EV_INIT_NOT_IN_U;
+        else if (D.v_ele[n] == 0) code = LTGPU_EV_INIT_NOT_IN_V;
+    }
+    if (!code) return;
+    int EF = D.P.ErrorFlag;
+    int gid = (int)(D.first_id + D.pid[n]);
+    if (EF < 1 || EF > 3) atomicMin(D.bad, gid);
+    else if (EF == 2) D.flags[n] |= LT_F_DEAD;
+    else D.flags[n] |= LT_F_OOB;
+    int k = atomicAdd(D.nev, 1);
+    if (k < D.evcap) { D.ev[k].particle = gid; D.ev[k].code = code; D.ev[k].time = 0.0; }
+    atomicAdd(cnt + (code - LTGPU_EV_INIT_OUT_MAIN), 1ull);
 }
 
 __global__ void k_fill_i32(int* p, int v, int n)
@@ -526,6 +569,40 @@ static int32_t make_gridtab(ltgpu_ctx* ctx, LtGridTab* G, int nE, int nodes, con
     TRY(upload(ctx, &G->node, nd.data(), nd.size()));
     TRY(upload(ctx, &G->adj, adj.data(), adj.size()));
     G->mask = dmask; G->nE = nE; G->nodes = nodes;
+    {   // bucket index for k_locate: about one element per bucket
+        double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+        for (int e = 0; e < nE; ++e)
+            for (int i = 0; i < 4; ++i) {
+                xmin = std::min(xmin, ele[(size_t)e * 8 + i]); xmax = std::max(xmax, ele[(size_t)e * 8 + i]);
+                ymin = std::min(ymin, ele[(size_t)e * 8 + 4 + i]); ymax = std::max(ymax, ele[(size_t)e * 8 + 4 + i]);
+            }
+        double cs = std::max(sqrt(std::max((xmax - xmin) * (ymax - ymin), 1e-18) / (double)nE), 1e-9);
+        while ((xmax - xmin) / cs * ((ymax - ymin) / cs) > 1.6e7) cs *= 1.5;
+        G->lx0 = xmin - cs; G->ly0 = ymin - cs; G->lrcs = 1.0 / cs;
+        G->lnx = (int)floor((xmax - G->lx0) * G->lrcs) + 2; G->lny = (int)floor((ymax - G->ly0) * G->lrcs) + 2;
+        std::vector<int> ptr((size_t)G->lnx * G->lny + 1, 0), idx;
+        auto range = [&](int e, int& cx0, int& cx1, int& cy0, int& cy1) {
+            const double* q = &ele[(size_t)e * 8];
+            double x0 = std::min({q[0], q[1], q[2], q[3]}), x1 = std::max({q[0], q[1], q[2], q[3]});
+            double y0 = std::min({q[4], q[5], q[6], q[7]}), y1 = std::max({q[4], q[5], q[6], q[7]});
+            cx0 = (int)floor((x0 - G->lx0) * G->lrcs); cx1 = (int)floor((x1 - G->lx0) * G->lrcs);
+            cy0 = (int)floor((y0 - G->ly0) * G->lrcs); cy1 = (int)floor((y1 - G->ly0) * G->lrcs);
+        };
+        for (int e = 0; e < nE; ++e) {
+            int cx0, cx1, cy0, cy1; range(e, cx0, cx1, cy0, cy1);
+            for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) ptr[(size_t)cy * G->lnx + cx + 1]++;
+        }
+        for (size_t c = 0; c + 1 < ptr.size(); ++c) ptr[c + 1] += ptr[c];
+        idx.resize(ptr.back());
+        std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+        for (int e = 0; e < nE; ++e) {                     // ascending e: every bucket list ascends
+            int cx0, cx1, cy0, cy1; range(e, cx0, cx1, cy0, cy1);
+            for (int cy = cy0; cy <= cy1; ++cy) for (int cx = cx0; cx <= cx1; ++cx) idx[fill[(size_t)cy * G->lnx + cx]++] = e;
+        }
+        if (idx.empty()) idx.push_back(0);
+        TRY(upload(ctx, &G->lptr, ptr.data(), ptr.size()));
+        TRY(upload(ctx, &G->lidx, idx.data(), idx.size()));
+    }
     return LTGPU_OK;
 }
 
@@ -706,6 +783,28 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
     }
     CK(cudaStreamSynchronize(ctx->compute));
     ctx->have_particles = true;
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_screen_initial(ltgpu_ctx* ctx, int64_t counts[5], int64_t* bad_particle)
+{
+    if (!ctx) return LTGPU_E_ARG;
+    ARG(ctx->have_particles && ctx->have_bounds, "screen_initial before set_particles / set_bounds");
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D;
+    CK(cudaMemsetAsync(ctx->d_stats, 0, 8 * sizeof(unsigned long long), ctx->compute));
+    k_screen<<<(D.n + 127) / 128, 128, 0, ctx->compute>>>(D, ctx->d_stats);
+    ctx->launches += 1;
+    unsigned long long c[8]; int bad = INT_MAX;
+    CK(cudaMemcpyAsync(c, ctx->d_stats, sizeof c, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaMemcpyAsync(&bad, ctx->d_bad, 4, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    if (counts) for (int k = 0; k < 5; ++k) counts[k] = (int64_t)c[k];
+    if (bad != INT_MAX) {
+        if (bad_particle) *bad_particle = bad;
+        ctx->err = "particle " + std::to_string(bad) + ": bad initial location and ErrorFlag outside 1..3 (the reference STOPs)";
+        return LTGPU_E_PARTICLE;
+    }
     return LTGPU_OK;
 }
 

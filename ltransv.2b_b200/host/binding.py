@@ -214,6 +214,15 @@ class LtransLib:
             self._check(rc, "run_external")
         return rc
 
+    def screen_initial(self):
+        """-> (rc, counts[5] for codes 11..15, lowest offending particle id or 0)"""
+        c = (C.c_int64 * 5)()
+        bad = C.c_int64(0)
+        rc = self._fn("screen_initial")(self.ctx, c, C.byref(bad))
+        if rc not in (LTGPU_OK, LTGPU_E_PARTICLE):
+            self._check(rc, "screen_initial")
+        return rc, np.array(list(c), dtype=np.int64), bad.value
+
     def sync(self):
         bad = C.c_int32(0)
         rc = self._fn("sync")(self.ctx, C.byref(bad))

@@ -14,8 +14,10 @@ from . import formats
 
 
 class Run:
-    def __init__(self, engine, world, prm, outdir, days, iprint, write_csv=True):
+    def __init__(self, engine, world, prm, outdir, days, iprint, write_csv=True, write_nc=False, NCOutFile="output",
+                 NCtime=0):
         self.e, self.w, self.prm, self.outdir = engine, world, prm, outdir
+        self.write_nc, self.NCOutFile, self.NCtime, self.nc = write_nc, NCOutFile, NCtime, None
         self.stepT = int(int(days * 86400) / prm.dt)            # LTRANS.f90:156-157
         self.iprint, self.write_csv = iprint, write_csv
         self.prcount, self.printdt = 1, 0                       # :290, :240
@@ -34,12 +36,28 @@ class Run:
         self.e.set_particles(x, y, z, dob, startpoly, r_ele, u_ele, v_ele, first_id=first_id)
         self.startpoly = startpoly
         self.first_id = first_id
+        head = {1: "The following particles were returned to their previous locations:", 2: "The following particles were killed:",
+                3: "The following particles were set out of bounds:"}.get(self.prm.ErrorFlag)      # :337-354
+        if head:
+            with open(os.path.join(self.outdir, "ErrorLog.txt"), "w") as f:
+                f.write(" " + head + "\n  \n")
+        rc, self.screened, bad = self.e.screen_initial()        # :356-452 start-up screen, on the device
+        self._errors()
+        if rc:
+            raise RuntimeError(f"particle {bad}: bad initial location (ErrorFlag outside 1..3: the reference STOPs)")
         for k in range(3):                                      # initHydro: back, centre, forward
             self.e.push_hydro(self.w.record(k))
+        if self.write_nc:                                       # :468-476 createNetCDF(par(:,pDOB)), first print at t = 0
+            from .roms_io import ParticleNetCDF
+            self.nc = ParticleNetCDF(self.outdir, self.NCOutFile, len(x), self.NCtime, self.prm.SaltTempOn,
+                                     self.prm.TrackCollisions)
+            self.nc.create(dob)
+            zero = np.zeros(len(x))                             # :292-309 initial state at model time 0
+            self.nc.write(0, zero, lon, lat, z, np.full(len(x), float(self.prm.Behavior)), zero, zero, zero, zero)
         if self.prm.TrackCollisions:                            # :461-466 header lines
-            for name in ("LandHits.csv", "BottomHits.csv"):
+            for name, col in (("LandHits.csv", "hitLand"), ("BottomHits.csv", "hitBottom")):
                 with open(os.path.join(self.outdir, name), "w") as f:
-                    f.write("numpar,lon,lat,depth,age,time,hits\n")
+                    f.write(" numpar,lon,lat,depth,age,time,%s\n" % col)       # list-directed: leading blank
 
     def run(self):
         stepIT = self.prm.dt // self.prm.idt
@@ -77,6 +95,9 @@ class Run:
             st = self.prm.SaltTempOn
             formats.write_para_csv(formats.para_filename(self.prcount, self.outdir), f["z"], f["status"], lon, lat,
                                    f["salt"] if st else None, f["temp"] if st else None)
+        if self.nc is not None:                                 # :1754-1775 writeNetCDF(int(ix(3)), ...)
+            self.nc.write(int(ix3), f["age"], lon, lat, f["z"], f["status"].astype(np.float64), f["hitBottom"], f["hitLand"],
+                          f["salt"], f["temp"])
         if self.prm.TrackCollisions:
             ids = self.first_id + np.arange(len(lon))
             formats.append_hits(os.path.join(self.outdir, "LandHits.csv"), ids, lon, lat, f["z"], f["age"], ix3, f["hitLand"])
@@ -95,4 +116,6 @@ class Run:
                 sp = np.zeros(len(lon), np.int32)
             formats.write_endfile(os.path.join(self.outdir, "endfile.csv"), f["status"], lat, lon, f["lifespan"],
                                   sp, f["endpoly"] if self.prm.settlementon else None)
+        if self.nc is not None:
+            self.nc.close()
         return f

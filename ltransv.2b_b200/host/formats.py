@@ -162,6 +162,11 @@ def append_hits(path, ids, lon, lat, z, age, time_s, hits):
 
 
 _EVENT_TEXT = {
+    11: "Particle %10d initially outside main bounds",          # LTRANS.f90:377, 400, 446-450: no time
+    12: "Particle %10d initially inside island bounds",
+    13: "Particle %10d initially not in rho element",
+    14: "Particle %10d initially not in u element",
+    15: "Particle %10d initially not in v element",
     21: "Particle %10d not in rho element after %10d seconds",
     22: "Particle %10d not in u element after %10d seconds",
     23: "Particle %10d not in v element after %10d seconds",
@@ -178,4 +183,4 @@ def append_errorlog(path, events):
     """ErrorLog.txt, formats 21-29 (LTRANS.f90:761-775); events = [(particle, code, time)]"""
     with open(path, "a") as f:
         for pid, code, t in events:
-            f.write(_EVENT_TEXT[code] % (pid, int(t)) + "\n")
+            f.write((_EVENT_TEXT[code] % pid if code < 20 else _EVENT_TEXT[code] % (pid, int(t))) + "\n")

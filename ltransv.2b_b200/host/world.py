@@ -206,7 +206,7 @@ class World:
     # ---------------------------------------------------------------- bounds --
     def bounds(self):
         """Marching-squares boundary tracer (see module docstring)."""
-        ni, nj, m = self.ni, self.nj, self.mask_rho
+        ni, nj, m = self.ni, self.nj, getattr(self, "mask_bnd", self.mask_rho)
         s = m.copy()
         s[0, :] = 0; s[-1, :] = 0; s[:, 0] = 0; s[:, -1] = 0
         ring = np.zeros_like(m, dtype=bool)

@@ -1316,6 +1316,33 @@ int32_t ora_run_external(ora_ctx* c, int32_t p)
     return LTGPU_OK;
 }
 
+/* The start-up screen of ini_LTRANS (LTRANS.f90:356-452): mbounds, ibounds, then the element
+ * check after setEle_all.  The reference reports only the first unlocated particle (its
+ * setEle_all leaves the loop, hydro:1594); every one is reported here. */
+int32_t ora_screen_initial(ora_ctx* c, int64_t counts[5], int64_t* bad_particle)
+{
+    int EF = c->prm.ErrorFlag;
+    int64_t cnt[5] = {0, 0, 0, 0, 0};
+    for (int n = 0; n < c->n; ++n) {
+        int code = 0; double island = 0.0;
+        if (ora_mbounds(c, c->Y[n], c->X[n]) == 0) code = LTGPU_EV_INIT_OUT_MAIN;               /* :362 */
+        else if (ora_ibounds(c, c->Y[n], c->X[n], &island) == 1) code = LTGPU_EV_INIT_IN_ISLAND; /* :385 */
+        else if (c->r_ele[n] == 0) code = LTGPU_EV_INIT_NOT_IN_RHO;                              /* :412-452 */
+        else if (c->u_ele[n] == 0) code = LTGPU_EV_INIT_NOT_IN_U;
+        else if (c->v_ele[n] == 0) code = LTGPU_EV_INIT_NOT_IN_V;
+        if (!code) continue;
+        int gid = (int)(c->first_id + n);
+        if (EF < 1 || EF > 3) { if (c->bad_particle == 0 || gid < c->bad_particle) c->bad_particle = gid; }
+        else if (EF == 2) c->dead[n] = 1;                                                        /* die */
+        else c->oob[n] = 1;                                                                      /* setOut */
+        add_event(c, gid, code, 0.0);
+        cnt[code - LTGPU_EV_INIT_OUT_MAIN]++;
+    }
+    if (counts) memcpy(counts, cnt, sizeof cnt);
+    if (c->bad_particle) { if (bad_particle) *bad_particle = c->bad_particle; return LTGPU_E_PARTICLE; }
+    return LTGPU_OK;
+}
+
 int32_t ora_sync(ora_ctx* c, int32_t* bad)
 {
     if (bad) *bad = c->bad_particle;

@@ -48,15 +48,15 @@ def test_particle_csv_round_trip(tmp_path):
     assert list(formats.read_particles_csv(p, False)[4]) == [0, 0]
 
 
-def run_driver(engine, outdir, n=120, **kw):
-    w = World(**SMALL)
+def run_driver(engine, outdir, n=120, world=None, run_kw=None, **kw):
+    w = world or World(**SMALL)
     base = dict(Behavior=4, HTurbOn=1, VTurbOn=0, pediage=3600.0, deadage=9000.0, SaltTempOn=1,
                 TrackCollisions=1, ErrorFlag=1)
     base.update(kw)
     prm = make_params(w, n, **base)
     x, y, z, dob, r, u, v = w.seed_particles(n, seed=77)
     lon, lat = w.proj.x2lon(x, y), w.proj.y2lat(y)
-    run = Run(engine, w, prm, outdir, days=3 / 24.0, iprint=1800)
+    run = Run(engine, w, prm, outdir, days=3 / 24.0, iprint=1800, **(run_kw or {}))
     run.init(lon, lat, z, dob, startpoly=np.full(n, 101001, np.int32))
     f = run.run()
     return run, f
@@ -77,4 +77,31 @@ def test_run_loop_writes_reference_formats(tmp_path):
     st = np.array([int(s.split(",")[2]) for s in end])
     assert set(st) <= {4, 2, -1, -2, -3} and (st == -2).sum() == (f["status"] == -2).sum()
     hits = open(os.path.join(out, "LandHits.csv")).read().splitlines()
-    assert hits[0].startswith("numpar") and all(len(s.split(",")) == 7 for s in hits[1:])
+    assert hits[0] == " numpar,lon,lat,depth,age,time,hitLand" and all(len(s.split(",")) == 7 for s in hits[1:])
+
+
+def test_run_loop_from_netcdf_files(tmp_path):
+    """The same run fed from ROMS grid / history NetCDF files (file sequencing of updateHydro) and
+    writing the particle NetCDF output next to the CSVs: identical CSVs, NetCDF rows = CSV rows."""
+    from oracle.oracle import Oracle
+    from scipy.io import netcdf_file
+    from ltrans_b200.host import roms_io
+    w = World(**SMALL)
+    roms_io.write_grid_nc(str(tmp_path / "grid.nc"), w)
+    roms_io.write_history_nc(w, str(tmp_path / "his_"), ".nc", 1, 4, nrec=5, tdim=2)
+    rw = roms_io.RomsWorld(str(tmp_path / "grid.nc"), str(tmp_path / "his_"), ".nc", 1, 4, tdim=2)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    run_driver(Oracle(), a, n=60)
+    run_driver(Oracle(), b, n=60, world=rw, run_kw=dict(write_nc=True, NCOutFile="out"))
+    rw.close()
+    for name in sorted(os.listdir(a)):
+        assert open(os.path.join(a, name)).read() == open(os.path.join(b, name)).read(), name
+    with netcdf_file(os.path.join(b, "out.nc"), "r", mmap=False) as f:
+        t = f.variables["model_time"][:]
+        assert np.array_equal(t, np.arange(0, 3 * 3600 + 1, 1800.0))          # t = 0 plus 6 prints
+        assert np.all(f.variables["color"][0] == 4.0) and np.all(f.variables["age"][0] == 0.0)
+        last = np.loadtxt(os.path.join(b, "para10000007.csv"), delimiter=",")
+        assert np.allclose(f.variables["depth"][-1], last[:, 0], rtol=0, atol=5.01e-4)
+        assert np.array_equal(f.variables["color"][-1], last[:, 1])
+        assert np.allclose(f.variables["lon"][-1], last[:, 2], rtol=0, atol=5.01e-5)
+        assert np.allclose(f.variables["salinity"][-1], last[:, 4], rtol=0, atol=5.01e-5)

@@ -189,6 +189,29 @@ def test_driver_outputs_match(tmp_path):
             assert open(os.path.join(og, name)).read().splitlines()[0] == open(os.path.join(oo, name)).read().splitlines()[0]
 
 
+def test_driver_from_netcdf_files(tmp_path):
+    """CUDA engine fed from ROMS grid / history NetCDF files (tdim = 2 records per file) and writing
+    the particle NetCDF file: same CSVs as the run fed from memory."""
+    from scipy.io import netcdf_file
+    from test_formats import run_driver
+    from ltrans_b200.host import roms_io
+    w = World(**SMALL)
+    roms_io.write_grid_nc(str(tmp_path / "grid.nc"), w)
+    roms_io.write_history_nc(w, str(tmp_path / "his_"), ".nc", 1, 4, nrec=5, tdim=2, startfile=True)
+    rw = roms_io.RomsWorld(str(tmp_path / "grid.nc"), str(tmp_path / "his_"), ".nc", 1, 4, tdim=2, startfile=True)
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    run_driver(LtransLib(), a)
+    run_driver(LtransLib(), b, world=rw, run_kw=dict(write_nc=True, NCOutFile="out"))
+    rw.close()
+    for name in sorted(os.listdir(a)):
+        assert open(os.path.join(a, name)).read() == open(os.path.join(b, name)).read(), name
+    with netcdf_file(os.path.join(b, "out.nc"), "r", mmap=False) as f:
+        assert f.variables["lon"][:].shape == (7, 120)
+        last = np.loadtxt(os.path.join(b, "para10000007.csv"), delimiter=",")
+        assert np.allclose(f.variables["depth"][-1], last[:, 0], rtol=0, atol=5.01e-4)
+        assert np.array_equal(f.variables["color"][-1], last[:, 1])
+
+
 GULF = dict(ni=48, nj=40, us=36, hmin=40.0, hmax=600.0, dlon=0.02, dlat=0.018, speed=0.9)
 
 

@@ -16,7 +16,15 @@ prm = make_params(w, n, Behavior=6, sink=0.002, settlementon=0, mortality=0, Tra
 g = LtransLib().create(prm)
 g.set_grid(w.grid()); g.set_bounds(w.bounds())
 x, y, z, dob, r, u, v = w.seed_particles(n)
-g.set_particles(x, y, z, dob, None, r, u, v)
+t1 = time.time()
+g.set_particles(x, y, z, dob, None, None, None, None)             # located on the device (element buckets)
+t2 = time.time()
+rc, counts, bad = g.screen_initial()
+t3 = time.time()
+e = g.fetch(("r_ele", "u_ele", "v_ele"))
+print("device locate + upload %.2f s, start-up screen %.3f s, elements == host locate: %s, screened %s" % (
+    t2 - t1, t3 - t2, bool(np.array_equal(e["r_ele"], r) and np.array_equal(e["u_ele"], u) and np.array_equal(e["v_ele"], v)),
+    counts.tolist()), flush=True)
 recs = [w.record(k) for k in range(4)]
 for k in range(3):
     g.push_hydro(recs[k])
