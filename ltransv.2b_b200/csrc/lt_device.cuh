@@ -10,6 +10,20 @@
 #include <math.h>
 #include "lt_types.h"
 
+#ifdef LT_DEBUG_TRACE
+__device__ unsigned long long g_dbgcnt[8];          // debug builds only: solver-cap census
+__device__ unsigned long long g_dbgcnt2[8];         // VTurb build census
+__device__ unsigned long long g_dbghist[64];        // VTurb walk: intervals above / below the first one
+__device__ double g_dbgcase[8];                      // inputs of the last secant-cap case
+#define LT_DBG_COUNT(k) atomicAdd(&g_dbgcnt[k], 1ull)
+#define LT_DBG_MAX(k, v) atomicMax(&g_dbgcnt[k], (unsigned long long)(v))
+#define LT_ASSERT(c) do { if (!(c)) atomicMax(&g_dbgcnt[7], (unsigned long long)__LINE__); } while (0)   /* index checks */
+#else
+#define LT_DBG_COUNT(k)
+#define LT_DBG_MAX(k, v)
+#define LT_ASSERT(c)
+#endif
+
 #define LT_DEV __device__ __forceinline__
 #define LT_DEVN __device__ __noinline__
 
@@ -164,9 +178,11 @@ LT_DEVN bool gridcell(const double* __restrict__ q, double X, double Y)
 #endif
 LT_FE_ATTR bool find_element(const LtGridTab& G, double X, double Y, int& ele)
 {
+    LT_ASSERT(ele >= 1 && ele <= G.nE);
     const int* row = G.adj + (size_t)(ele - 1) * 10;
     for (int i = 0; i < 10; ++i) {
         int check = __ldg(row + i);
+        LT_ASSERT(check >= 0 && check <= G.nE);
         if (check == 0) return false;
         if (gridcell(G.ele + (size_t)(check - 1) * 8, X, Y)) { ele = check; return true; }
     }
@@ -403,17 +419,6 @@ LT_DEV double sig_guess(double T)
 // One Newton iteration of the convexity equation  SIG * T1(SIG) = TP1  (tension:528-579).
 // Returns true when the loop of the reference would exit; `out` is then the tension factor
 // (0 with err = 1 when the reference would raise SigErr).  State: SIG, NIT, chk, chk_at.
-#ifdef LT_DEBUG_TRACE
-__device__ unsigned long long g_dbgcnt[8];          // debug builds only: solver-cap census
-__device__ unsigned long long g_dbgcnt2[8];         // VTurb build census
-__device__ unsigned long long g_dbghist[64];        // VTurb walk: intervals above / below the first one
-__device__ double g_dbgcase[8];                      // inputs of the last secant-cap case
-#define LT_DBG_COUNT(k) atomicAdd(&g_dbgcnt[k], 1ull)
-#define LT_DBG_MAX(k, v) atomicMax(&g_dbgcnt[k], (unsigned long long)(v))
-#else
-#define LT_DBG_COUNT(k)
-#define LT_DBG_MAX(k, v)
-#endif
 struct NewtonState { double SIG, TP1, chk; int NIT, chk_at; };
 LT_DEV void newton_start(NewtonState& q, double TP1, double SIG0) { q.SIG = SIG0; q.TP1 = TP1; q.chk = SIG0; q.NIT = 0; q.chk_at = 1; }
 LT_DEV bool newton_step(NewtonState& q, double& out, int& err)
@@ -773,6 +778,7 @@ LT_DEVN int test_settlement(const LtDev& D, double P_age, int R_ele, double Px, 
 {
     if (!(P_age >= D.P.pediage)) return 0;           // settletime = P_pediage (behavior:154)
     int polyin = 0, pidx = -1;
+    LT_ASSERT(R_ele >= 1 && R_ele <= D.R.nE);
     for (int q = __ldg(D.elepoly_ptr + R_ele - 1); q < __ldg(D.elepoly_ptr + R_ele); ++q) {
         int pi = __ldg(D.elepoly_idx + q);
         int start = __ldg(D.poly_start + pi), size = __ldg(D.poly_size + pi);

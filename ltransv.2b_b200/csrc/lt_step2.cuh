@@ -177,6 +177,7 @@ LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, do
     }
     int ii = level_window2<false>(D, col, Zpar, us);
     int iii = level_window2<true>(D, col, Zpar, ws);
+    LT_ASSERT(ii >= 1 && ii + 3 <= us && iii >= 1 && iii + 3 <= ws);
     {
         const T* f2[2] = {fu, fv}; const Stencil* s2[2] = {&s.u, &s.v}; const int g2[2] = {G_U, G_V};
         double o[2];
@@ -513,6 +514,7 @@ struct VtCtx {
     struct Seg { double slope, icpt, znext; int lev; };
     LT_DEV void seg_load(Seg& g, int t, int lev) const
     {   // lev = jlo (1-based)
+        LT_ASSERT(lev >= 1 && lev <= ws - 1);
         double zlo = zl[t][lev - 1], zhi = zl[t][lev], klo = khp[t][lev - 1], khi = khp[t][lev];
         g.lev = lev; g.slope = qdiv(klo - khi, zlo - zhi); g.icpt = klo - g.slope * zlo; g.znext = zhi;   // :126-133
     }
@@ -528,6 +530,7 @@ struct VtCtx {
     LT_DEVN void build(int ka_)
     {
         ka = ka_; kb = min(p2, ka + VW - 1);
+        LT_ASSERT(ka >= 1 && kb - ka >= 3 && kb - ka < VW);
 #ifdef LT_DEBUG_TRACE
         atomicAdd(&g_dbgcnt2[0], 1ull);                  // builds
 #endif
@@ -584,7 +587,7 @@ struct VtCtx {
             double sigma, TP1, SIG0; int e = 0;
             if (sigs_classify(knot_x(k + 1) - knot_x(k), fy[k - ka], fy[k + 1 - ka], yp[k - ka], yp[k + 1 - ka], sigma, TP1, SIG0, e))
                 sg[k - ka] = sigma;
-            else { sg[k - ka] = SIG0; tp[np] = TP1; pend[np] = (unsigned char)(k - ka); ++np; }
+            else { LT_ASSERT(np < VW && k - ka >= 0 && k - ka < VW); sg[k - ka] = SIG0; tp[np] = TP1; pend[np] = (unsigned char)(k - ka); ++np; }
             if (e) sigerr = true;
         }
         // one Newton loop per lane over all its pending intervals (see wcts2)
@@ -661,6 +664,7 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
         if (cI >= 0 && zq >= cX1 && zq < cX2) return;                  // still inside [X(I), X(I+1)): INTRVL gives I
         int I = V.interval(zq); V.need(I);
         int q = I - V.ka;
+        LT_ASSERT(I >= V.ia && I <= V.ib && q >= 0 && q + 1 < VW && I >= 1 && I <= V.p2 - 1);
         cI = I; cX1 = V.knot_x(I); cX2 = V.knot_x(I + 1);
 #ifdef LT_DEBUG_TRACE
         if (dI0 < 0) dI0 = I; dImin = min(dImin, I); dImax = max(dImax, I);
