@@ -219,6 +219,15 @@ int32_t ltgpu_fetch(ltgpu_ctx* ctx,
     double* salt, double* temp, int32_t* hitBottom, int32_t* hitLand,
     int32_t* endpoly, double* lifespan,
     int32_t* r_ele, int32_t* u_ele, int32_t* v_ele);
+/* Diagnostic (no reference counterpart): how many times each particle's water-column
+ * profile fell back from the tension spline to linint because SIGS raised SigErr
+ * (hydro:2621-2644, ver_turb:300-336).  The reference takes that branch silently; its
+ * verdict hangs on the last bits of T = max(D1/D2, D2/D1) and of exp(), so two correct
+ * implementations disagree on WHICH steps fall back (about 4e-4 per particle-step) while
+ * agreeing on the rate; the parity tests use this count to show that every trajectory
+ * difference above 1e-9 belongs to a particle whose fall-back history differs. */
+int32_t ltgpu_fetch_sigerr(ltgpu_ctx* ctx, int32_t* count);
+
 /* Reset hitBottom/hitLand after a print (LTRANS.f90:1662-1665). */
 int32_t ltgpu_reset_hits(ltgpu_ctx* ctx);
 

@@ -463,12 +463,20 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
     const double SBIG = 85.0, RTOL = LT_RTOL, FTOL = 0.0;
     double S = qdiv(Y2 - Y1, DX);
     double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
+#ifdef LT_DEBUG_TRACE
+    atomicAdd(&g_dbgcnt2[7], 1ull);                                       // intervals classified
+#endif
     if ((D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0)) { sigma = SBIG; return true; }
     double SIG = 0.0;
     if (D1D2 >= 0.0) {
         if (D1D2 == 0.0) { sigma = 0.0; return true; }
         double T = fmax(qdiv(D1, D2), qdiv(D2, D1));
         if (T <= 2.0) { sigma = 0.0; return true; }
+#ifdef LT_DEBUG_TRACE
+        atomicAdd(&g_dbgcnt2[4], 1ull);                                   // convexity solves (T > 2)
+        if (T > 2.0245 && T < 2.047) atomicAdd(&g_dbgcnt2[5], 1ull);      // ... inside the band where the Newton loop can cycle
+        if (T > 2.02 && T < 2.10) atomicAdd(&g_dbgcnt2[6], 1ull);
+#endif
         TP1o = T + 1.0;
         SIG0 = sig_guess(T);                               // reference: SQRT(10 T - 20) (tension:524)
         return false;

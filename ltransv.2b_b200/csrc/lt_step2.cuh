@@ -102,16 +102,67 @@ LT_DEV double linint4(const Knots4& k, double y0, double y1, double y2, double y
     return m * T + (Y[jlo - 1] - m * k.x[jlo - 1]);
 }
 
+// The reference's SIGS sweeps ALL intervals of the profile and leaves at the first one whose
+// convexity Newton loop does not converge (SigErr, tension:556-559); WCTS_ITPI then replaces the
+// whole profile by linint (hydro:2621-2644) even when the failing interval is not the one that
+// holds the particle.  That loop's verdict is a pure function of T = max(D1/D2, D2/D1); scanned
+// over 8e7 values it fails only for T in [2.02498, 2.04625] (about 1e-3 of the doubles there,
+// around SIG = 0.5 where the two branches of the iteration meet), never outside.  So the other
+// intervals need the Newton loop only when their T lies in LT_BAND (1.4 % of intervals).
+#define LT_BAND_LO 2.02
+#define LT_BAND_HI 2.06
+LT_DEV bool sigerr_candidate(double s, double ypa, double ypb, double& T)
+{   // interval with chord slope s and end slopes ypa, ypb: convexity case with T in the band?
+    const double D1 = s - ypa, D2 = ypb - s;
+    if (!(D1 * D2 > 0.0)) return false;
+    const double a = fabs(D1), b = fabs(D2), hi = fmax(a, b), lo = fmin(a, b);
+    if (!(hi > LT_BAND_LO * lo && hi < LT_BAND_HI * lo)) return false;
+    T = fmax(qdiv(D1, D2), qdiv(D2, D1));
+    return T > 2.0;
+}
+
 // TSPSI(N=4) + HVAL (or the linint fallback) at T: the water-column profile value of
-// WCTS_ITPI (hydro:2619-2644).  Flattening the Newton solves of the 9 splines of one
-// find_currents into one loop (as VtCtx::build does) was tried and lost: the per-spline
-// state it has to keep (9 x 7 doubles) spills, see profiles/r01_notes.md.
-LT_DEVN double spline4_eval2(const Knots4& k, double y0, double y1, double y2, double y3, double T)
+// WCTS_ITPI (hydro:2619-2644).  One Newton loop per lane runs the solve of the interval that
+// holds T and the verdict-only solves of the other intervals.  (Flattening the solves of all 9
+// splines of one find_currents was tried and lost: 9 x 7 doubles of state spill.)
+LT_DEVN double spline4_eval2(const Knots4& k, double y0, double y1, double y2, double y3, double T, int& nsig)
 {
-    Iv4 v; spline4_prepare(k, y0, y1, y2, y3, T, v);
-    int err = 0;
-    double sig = sigs_interval(v.X2 - v.X1, v.Y1, v.Y2, v.P1, v.P2, err);
+    const double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
+    const double s1 = (y1 - y0) * k.r1, s2 = (y2 - y1) * k.r2, s3 = (y3 - y2) * k.r3;
+    const double p0 = ypc1_end(s1, s1 + d1 * (s1 - s2) * k.r12), p1 = ypc1_mid_r(d1, d2, s1, s2, k.r12);
+    const double p2 = ypc1_mid_r(d2, d3, s2, s3, k.r23), p3 = ypc1_end(s3, s3 + d3 * (s3 - s2) * k.r23);
+    const int I = (T < k.x[0]) ? 0 : (T > k.x[3]) ? 2 : (T < k.x[2] ? (T < k.x[1] ? 0 : 1) : 2);
+    Iv4 v;
+    v.X1 = I == 0 ? k.x[0] : I == 1 ? k.x[1] : k.x[2]; v.X2 = I == 0 ? k.x[1] : I == 1 ? k.x[2] : k.x[3];
+    v.Y1 = I == 0 ? y0 : I == 1 ? y1 : y2; v.Y2 = I == 0 ? y1 : I == 1 ? y2 : y3;
+    v.P1 = I == 0 ? p0 : I == 1 ? p1 : p2; v.P2 = I == 0 ? p1 : I == 1 ? p2 : p3;
+    int err = 0, np = 0;
+    double sig = 0.0, tq0 = 0.0, tq1 = 0.0, tq2 = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;       // pending (TP1, start) pairs
+    bool own = false;                                   // slot 0 is the interval that holds T
+    {
+        double TP1, SIG0;
+        if (!sigs_classify(v.X2 - v.X1, v.Y1, v.Y2, v.P1, v.P2, sig, TP1, SIG0, err)) { tq0 = TP1; g0 = SIG0; np = 1; own = true; }
+    }
+    {   // the two other intervals: verdict only
+        const double sa = I == 0 ? s2 : s1, pa = I == 0 ? p1 : p0, pb = I == 0 ? p2 : p1;
+        const double sb = I == 2 ? s2 : s3, pc = I == 2 ? p1 : p2, pd = I == 2 ? p2 : p3;
+        double Tq;
+        if (sigerr_candidate(sa, pa, pb, Tq)) { if (np == 0) { tq0 = Tq + 1.0; g0 = sig_guess(Tq); } else { tq1 = Tq + 1.0; g1 = sig_guess(Tq); } ++np; }
+        if (sigerr_candidate(sb, pc, pd, Tq)) { if (np == 0) { tq0 = Tq + 1.0; g0 = sig_guess(Tq); } else if (np == 1) { tq1 = Tq + 1.0; g1 = sig_guess(Tq); } else { tq2 = Tq + 1.0; g2 = sig_guess(Tq); } ++np; }
+    }
+    if (np > 0) {
+        int cur = 0; NewtonState ns; newton_start(ns, tq0, g0);
+        while (cur < np) {
+            double o; int e = 0;
+            if (newton_step(ns, o, e)) {
+                err |= e;
+                if (cur == 0 && own) sig = o;
+                if (++cur < np) newton_start(ns, cur == 1 ? tq1 : tq2, cur == 1 ? g1 : g2);
+            }
+        }
+    }
     if (err == 0) return hval_interval(T, v.X1, v.X2, v.Y1, v.Y2, v.P1, v.P2, sig);
+    ++nsig;
     return linint4(k, y0, y1, y2, y3, T);
 }
 
@@ -124,7 +175,7 @@ struct Stage2 { Stencil r, u, v; };
 #endif
 template <class T, int PH, bool W, int NF>
 LT_WCTS_ATTR void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st, const int* grid, int4 und, int L,
-                  const ColK& col, int deplvl, double P_zb, double P_zc, double P_zf, int v, double* out)
+                  const ColK& col, int deplvl, double P_zb, double P_zc, double P_zf, int v, double* out, int& nsig)
 {
     double vb[NF][4], vc[NF][4], vf[NF][4];
     Knots4 kb, kc, kf;
@@ -138,9 +189,9 @@ LT_WCTS_ATTR void wcts2(const LtDev& D, const T* const* fld, const Stencil* cons
     const double* w = v < 3 ? D.LW[v] : D.LW4;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        double pb = spline4_eval2(kb, vb[f][0], vb[f][1], vb[f][2], vb[f][3], P_zb);
-        double pc = spline4_eval2(kc, vc[f][0], vc[f][1], vc[f][2], vc[f][3], P_zc);
-        double pf = first ? 0.0 : spline4_eval2(kf, vf[f][0], vf[f][1], vf[f][2], vf[f][3], P_zf);
+        double pb = spline4_eval2(kb, vb[f][0], vb[f][1], vb[f][2], vb[f][3], P_zb, nsig);
+        double pc = spline4_eval2(kc, vc[f][0], vc[f][1], vc[f][2], vc[f][3], P_zc, nsig);
+        double pf = first ? 0.0 : spline4_eval2(kf, vf[f][0], vf[f][1], vf[f][2], vf[f][3], P_zf, nsig);
         out[f] = lag(w, pb, pc, pf);
     }
 }
@@ -149,7 +200,7 @@ LT_WCTS_ATTR void wcts2(const LtDev& D, const T* const* fld, const Stencil* cons
 template <class T, int PH>
 LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, double Zpar,
                             double P_zb, double P_zc, double P_zf, int version,
-                            double& Uad, double& Vad, double& Wad)
+                            double& Uad, double& Vad, double& Wad, int& nsig)
 {
     const int us = D.P.us, ws = D.P.ws;
     const double z0 = D.P.z0;
@@ -181,13 +232,13 @@ LT_DEVN void find_currents2(const LtDev& D, const Stage2& s, const ColK& col, do
     {
         const T* f2[2] = {fu, fv}; const Stencil* s2[2] = {&s.u, &s.v}; const int g2[2] = {G_U, G_V};
         double o[2];
-        wcts2<T, PH, false, 2>(D, f2, s2, g2, s.u.nd, us, col, ii, P_zb, P_zc, P_zf, version - 1, o);
+        wcts2<T, PH, false, 2>(D, f2, s2, g2, s.u.nd, us, col, ii, P_zb, P_zc, P_zf, version - 1, o, nsig);
         Uad = o[0]; Vad = o[1];
     }
     {
         const T* f1[1] = {fw}; const Stencil* s1[1] = {&s.r}; const int g1[1] = {G_RHO};
         double o[1];
-        wcts2<T, PH, true, 1>(D, f1, s1, g1, s.u.nd, ws, col, iii, P_zb, P_zc, P_zf, version - 1, o);
+        wcts2<T, PH, true, 1>(D, f1, s1, g1, s.u.nd, ws, col, iii, P_zb, P_zc, P_zf, version - 1, o, nsig);
         Wad = o[0];
     }
 }
@@ -242,7 +293,9 @@ LT_DEVN BehavOut behave(const LtDev& D, int n, const Stage2& s0, const ColK& col
         int deplvl = level_window2<false>(D, col, Zpar, P.us);
         const T* f1[1] = {(const T*)D.salt}; const Stencil* s1[1] = {&s0.r}; const int g1[1] = {G_RHO};
         double o1[1];
-        wcts2<T, PH, false, 1>(D, f1, s1, g1, s0.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o1);
+        int nsig = 0;
+        wcts2<T, PH, false, 1>(D, f1, s1, g1, s0.u.nd, P.us, col, deplvl, P_zb, P_zc, P_zf, 3, o1, nsig);
+        if (nsig) D.nsig[n] += nsig;
         P_S = o1[0];
     }
     uint4 rnd = philox(g, 0x80000000u);
@@ -369,6 +422,7 @@ LT_DEV void particle_error(const LtDev& D, int n, int code, double revertZ)
 struct AdvS {
     Stage2 st; ColK col;
     double Xpar, Ypar, Zpar, P_zb, P_zc, P_zf, P_depth, P_angle, ca, sa, minpd, maxpd, sU, sV, sW, xs, ys, zs;
+    int nsig;                       // SigErr fall-backs of this step's WCTS_ITPI calls
 };
 
 template <class T, int PH>
@@ -423,7 +477,7 @@ LT_DEV bool advect_prologue(const LtDev& D, int n, AdvS& S)
     S.ca = cos(P_angle); S.sa = sin(P_angle);
     S.Xpar = Xpar; S.Ypar = Ypar; S.Zpar = Zpar; S.P_zb = P_zb; S.P_zc = P_zc; S.P_zf = P_zf;
     S.P_depth = P_depth; S.P_angle = P_angle;
-    S.sU = 0.0; S.sV = 0.0; S.sW = 0.0; S.xs = Xpar; S.ys = Ypar; S.zs = Zpar;
+    S.nsig = 0; S.sU = 0.0; S.sV = 0.0; S.sW = 0.0; S.xs = Xpar; S.ys = Ypar; S.zs = Zpar;
     return true;
 }
 
@@ -434,7 +488,7 @@ LT_DEV void advect_stage(const LtDev& D, AdvS& S, int stg)
     const double eps6 = (double)kF32_1em6;
     double Uad, Vad, Wad;
     stage_weights2(S.st, S.xs, S.ys);
-    find_currents2<T, PH>(D, S.st, S.col, S.zs, S.P_zb, S.P_zc, S.P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad);
+    find_currents2<T, PH>(D, S.st, S.col, S.zs, S.P_zb, S.P_zc, S.P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad, S.nsig);
     const double wgt = (stg == 0 || stg == 3) ? 1.0 : 2.0;
     S.sU += wgt * Uad; S.sV += wgt * Vad; S.sW += wgt * Wad;
     if (stg < 3) {
@@ -463,7 +517,7 @@ LT_DEV void advect_epilogue(const LtDev& D, int n, AdvS& S)
         int deplvl = level_window2<false>(D, S.col, S.Zpar, P.us);
         const T* f2[2] = {(const T*)D.salt, (const T*)D.temp}; const Stencil* s2[2] = {&S.st.r, &S.st.r}; const int g2[2] = {G_RHO, G_RHO};
         double o[2];
-        wcts2<T, PH, false, 2>(D, f2, s2, g2, S.st.u.nd, P.us, S.col, deplvl, S.P_zb, S.P_zc, S.P_zf, 3, o);
+        wcts2<T, PH, false, 2>(D, f2, s2, g2, S.st.u.nd, P.us, S.col, deplvl, S.P_zb, S.P_zc, S.P_zf, 3, o, S.nsig);
         D.psalt[n] = o[0]; D.ptemp[n] = o[1];
     }
     if (P.HTurbOn) {                                                     // hor_turb_module.f90:29-50
@@ -479,6 +533,7 @@ LT_DEV void advect_epilogue(const LtDev& D, int n, AdvS& S)
     D.s_nx[n] = newX; D.s_ny[n] = newY; D.s_advz[n] = idt * P_W;
     D.s_pu[n] = P_U; D.s_pv[n] = P_V; D.s_turbv[n] = 0.0;
     D.s_act[n] = 1;
+    if (S.nsig) D.nsig[n] += S.nsig;
 }
 
 // ============================================================= kernel 2: VTurb ==
@@ -699,6 +754,7 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
 #ifdef LT_DEBUG_TRACE
     if (dI0 >= 0) { atomicAdd(&g_dbghist[min(dImax - dI0, 31)], 1ull); atomicAdd(&g_dbghist[32 + min(dI0 - dImin, 31)], 1ull); }
 #endif
+    if (V.sigerr) D.nsig[n] += 1;
     D.s_turbv[n] = P_zc - ParZc;                                        // :342
 }
 

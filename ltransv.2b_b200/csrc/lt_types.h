@@ -47,6 +47,7 @@ struct LtDev {
     // particles (SoA)
     double *x, *y, *z, *age, *dob, *lifespan, *psalt, *ptemp, *timer, *sprev, *zprev;
     int *r_ele, *u_ele, *v_ele, *hitB, *hitL, *endpoly;
+    int *nsig;                  // [n] diagnostic: SigErr (linint) fall-backs taken so far
     uint8_t* flags;             // bit0 settled, bit1 dead, bit2 oob, bit3 bottom (behaviour 7)
     int8_t* behave;             // P_behave
     int n; long long first_id;

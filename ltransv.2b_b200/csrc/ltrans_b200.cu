@@ -439,7 +439,7 @@ static int32_t resort(ltgpu_ctx* ctx)
     ctx->launches += 2;
     double** a8[] = {&D.x, &D.y, &D.z, &D.age, &D.dob, &D.lifespan, &D.psalt, &D.ptemp, &D.timer, &D.sprev, &D.zprev};
     for (auto p : a8) permute(ctx, p, &ctx->spare8);
-    int** a4[] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly, &ctx->d_pid};
+    int** a4[] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly, &D.nsig, &ctx->d_pid};
     for (auto p : a4) permute(ctx, p, &ctx->spare4);
     permute(ctx, &D.flags, &ctx->spare1);
     { uint8_t* b = (uint8_t*)D.behave; permute(ctx, &b, &ctx->spare1); D.behave = (int8_t*)b; }
@@ -735,7 +735,7 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
     size_t N = (size_t)n;
     double** dd[] = {&D.x, &D.y, &D.z, &D.age, &D.dob, &D.lifespan, &D.psalt, &D.ptemp, &D.timer, &D.sprev, &D.zprev};
     for (auto p : dd) { TRY(dalloc(ctx, p, N)); CK(cudaMemsetAsync(*p, 0, N * 8, ctx->compute)); }
-    int** ii[] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly};
+    int** ii[] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly, &D.nsig};
     for (auto p : ii) { TRY(dalloc(ctx, p, N)); CK(cudaMemsetAsync(*p, 0, N * 4, ctx->compute)); }
     TRY(dalloc(ctx, &D.flags, N)); TRY(dalloc(ctx, &D.behave, N));
     CK(cudaMemsetAsync(D.flags, ctx->prm.Behavior == 7 ? LT_F_BOTTOM : 0, N, ctx->compute));   // behavior:113
@@ -954,6 +954,15 @@ int32_t ltgpu_fetch(ltgpu_ctx* ctx, double* x, double* y, double* z, double* age
     TRY(fetch_col(ctx, endpoly, (const int*)D.endpoly)); TRY(fetch_col(ctx, lifespan, (const double*)D.lifespan));
     TRY(fetch_col(ctx, r_ele, (const int*)D.r_ele)); TRY(fetch_col(ctx, u_ele, (const int*)D.u_ele)); TRY(fetch_col(ctx, v_ele, (const int*)D.v_ele));
     (void)N; (void)s;
+    return fetch_flush(ctx);
+}
+
+int32_t ltgpu_fetch_sigerr(ltgpu_ctx* ctx, int32_t* count)
+{
+    if (!ctx || !count) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "fetch_sigerr before set_particles");
+    CK(cudaSetDevice(ctx->device));
+    TRY(fetch_col(ctx, count, (const int*)ctx->D.nsig));
     return fetch_flush(ctx);
 }
 

@@ -243,6 +243,12 @@ class LtransLib:
         self._check(rc, "fetch")
         return {k: v for k, v in out.items() if v is not None}
 
+    def fetch_sigerr(self):
+        """diagnostic: SigErr (linint) fall-backs per particle so far"""
+        c = np.zeros(self.n, dtype=np.int32)
+        self._check(self._fn("fetch_sigerr")(self.ctx, _p(c)), "fetch_sigerr")
+        return c
+
     def reset_hits(self):
         self._check(self._fn("reset_hits")(self.ctx), "reset_hits")
 

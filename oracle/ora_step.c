@@ -51,6 +51,7 @@ struct ora_ctx {
     int n; int64_t first_id;
     double *X, *Y, *Z, *nX, *nY, *nZ, *DOB, *Age, *Lifespan, *P_Salt, *P_Temp;
     int32_t *startpoly, *endpoly, *hitBottom, *hitLand, *r_ele, *u_ele, *v_ele;
+    int32_t *nsig;                    /* diagnostic: SigErr fall-backs per particle */
     double *timer, *P_Sprev, *P_zprev, *P_swim3;
     int32_t *P_behave; uint8_t *bottom, *dead, *oob, *settle;
     /* events / stop */
@@ -249,6 +250,7 @@ int32_t ora_set_particles(ora_ctx* c, int32_t n, int64_t first_id,
 #define ZALLOC(p, T) do { free(p); (p) = (T*)calloc((size_t)n, sizeof(T)); } while (0)
     ZALLOC(c->Age, double); ZALLOC(c->Lifespan, double); ZALLOC(c->P_Salt, double); ZALLOC(c->P_Temp, double);
     ZALLOC(c->startpoly, int32_t); ZALLOC(c->endpoly, int32_t); ZALLOC(c->hitBottom, int32_t);
+    ZALLOC(c->nsig, int32_t);
     ZALLOC(c->hitLand, int32_t); ZALLOC(c->r_ele, int32_t); ZALLOC(c->u_ele, int32_t); ZALLOC(c->v_ele, int32_t);
     ZALLOC(c->timer, double); ZALLOC(c->P_Sprev, double); ZALLOC(c->P_zprev, double); ZALLOC(c->P_swim3, double);
     ZALLOC(c->P_behave, int32_t); ZALLOC(c->bottom, uint8_t); ZALLOC(c->dead, uint8_t);
@@ -554,6 +556,10 @@ static double interp(ora_ctx* c, const elestate* es, double xp, double yp, int f
     return vp;
 }
 
+/* diagnostic only: SigErr (linint) fall-backs that reached a result during the current
+ * particle-step; summed per particle for ora_fetch_sigerr */
+static __thread int tl_nsig;
+
 /* ---- WCTS_ITPI (hydro:2577-2689) ------------------------------------------ */
 static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, double Ypos, int deplvl,
     const double* Pwc_zb, const double* Pwc_zc, const double* Pwc_zf,
@@ -573,13 +579,13 @@ static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, do
     int IER, SigErr;
     SigErr = 0; ora_tspsi(nN, abb_zb, abb_vb, YP, SIGM, &IER, &SigErr);
     if (SigErr == 0) P_vb = ora_hval(P_zb, nN, abb_zb, abb_vb, YP, SIGM, &IER);
-    else ora_linint(abb_zb, abb_vb, nN, P_zb, &P_vb, &slope);
+    else { ora_linint(abb_zb, abb_vb, nN, P_zb, &P_vb, &slope); tl_nsig++; }
     SigErr = 0; ora_tspsi(nN, abb_zc, abb_vc, YP, SIGM, &IER, &SigErr);
     if (SigErr == 0) P_vc = ora_hval(P_zc, nN, abb_zc, abb_vc, YP, SIGM, &IER);
-    else ora_linint(abb_zc, abb_vc, nN, P_zc, &P_vc, &slope);
+    else { ora_linint(abb_zc, abb_vc, nN, P_zc, &P_vc, &slope); tl_nsig++; }
     SigErr = 0; ora_tspsi(nN, abb_zf, abb_vf, YP, SIGM, &IER, &SigErr);
     if (SigErr == 0) P_vf = ora_hval(P_zf, nN, abb_zf, abb_vf, YP, SIGM, &IER);
-    else ora_linint(abb_zf, abb_vf, nN, P_zf, &P_vf, &slope);
+    else { ora_linint(abb_zf, abb_vf, nN, P_zf, &P_vf, &slope); if (p != 1) tl_nsig++; }   /* unused when p == 1 */
     double ey[3];
     if (p == 1) { ey[0] = P_vb; ey[1] = P_vb; ey[2] = P_vc; }      /* ledger 8 */
     else        { ey[0] = P_vb; ey[1] = P_vc; ey[2] = P_vf; }
@@ -720,6 +726,7 @@ static double VTurb(ora_ctx* c, const elestate* es, prng* g, double P_zc, double
     }
     int IER, SigErr = 0;
     ora_tspsi(p2, fx, fy, YPK, SIGK, &IER, &SigErr);         /* :278-279 */
+    if (SigErr != 0) tl_nsig++;
     double deltat = 2.0;
     int loop = c->prm.idt / (int)deltat;                     /* :283 */
     double ParZc = P_zc;
@@ -1293,10 +1300,13 @@ int32_t ora_step(ora_ctx* c, int32_t p, int32_t it)
     int stop = 0;
     if (c->nthreads > 1 && c->rng_mode == ORA_RNG_PHILOX) {
 #pragma omp parallel for schedule(dynamic, 256) num_threads(c->nthreads) reduction(| : stop)
-        for (int n = 0; n < c->n; ++n) stop |= step_particle(c, n, p, it, ex, ix, gstep);
+        for (int n = 0; n < c->n; ++n) { tl_nsig = 0; stop |= step_particle(c, n, p, it, ex, ix, gstep); c->nsig[n] += tl_nsig; }
     } else {
         for (int n = 0; n < c->n; ++n) {
-            if (step_particle(c, n, p, it, ex, ix, gstep)) { stop = 1; break; }   /* STOP */
+            tl_nsig = 0;
+            int st_ = step_particle(c, n, p, it, ex, ix, gstep);
+            c->nsig[n] += tl_nsig;
+            if (st_) { stop = 1; break; }   /* STOP */
         }
     }
     if (!stop) for (int n = 0; n < c->n; ++n) {                          /* :1407-1414 */
@@ -1340,6 +1350,12 @@ int32_t ora_screen_initial(ora_ctx* c, int64_t counts[5], int64_t* bad_particle)
     }
     if (counts) memcpy(counts, cnt, sizeof cnt);
     if (c->bad_particle) { if (bad_particle) *bad_particle = c->bad_particle; return LTGPU_E_PARTICLE; }
+    return LTGPU_OK;
+}
+
+int32_t ora_fetch_sigerr(ora_ctx* c, int32_t* count)
+{
+    memcpy(count, c->nsig, sizeof(int32_t) * (size_t)c->n);
     return LTGPU_OK;
 }
 

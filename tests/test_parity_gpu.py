@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 PASSIVE = dict(HTurbOn=0, VTurbOn=0, Behavior=0, settlementon=0, mortality=0)
 
 
-def _pair(n, nexternal, nint=None, world_kw=SMALL, dob_max=0.0, locate=True, dtype=np.float32, **kw):
+def _pair(n, nexternal, nint=None, world_kw=SMALL, dob_max=0.0, locate=True, dtype=np.float32, sigerr=False, **kw):
     from oracle.oracle import Oracle
     w = World(**world_kw)
     prm = make_params(w, n, **kw)
@@ -32,8 +32,9 @@ def _pair(n, nexternal, nint=None, world_kw=SMALL, dob_max=0.0, locate=True, dty
     res = compare(fg, fo, w)
     ev = (g.drain_events(), o.drain_events())
     st = (g.stats(), o.stats())
+    sig = (g.fetch_sigerr(), o.fetch_sigerr()) if sigerr else ()
     g.destroy(); o.destroy()
-    return rg, ro, res, ev, st, fg, fo
+    return (rg, ro, res, ev, st, fg, fo) + sig
 
 
 CASES = {
@@ -92,15 +93,16 @@ def test_errorflag0_stops_on_lowest_particle():
 
 
 def test_vturb_same_stream_short_horizon():
-    """Same Philox stream, 4 internal steps.  The reference's SIGS Newton loop (tension:528-579)
-    stops on |F| <= 200 eps, which is at the rounding-noise level of F itself: in rare columns
-    (order 1e-3 of particle-steps) whether it converges or raises SigErr -- which swaps the whole
-    column's spline for linint -- is decided by the last bit of exp().  Those columns differ
-    between ANY two libms (glibc here, CUDA on the device, the Fortran runtime in the
-    reference); everything else must agree to 1e-9."""
-    rg, ro, res, ev, st, fg, fo = _pair(2000, 1, nint=4, **dict(PASSIVE, HTurbOn=1, VTurbOn=1))
+    """Same Philox stream, 4 internal steps of HTurb + VTurb.  The only branch on which CUDA and
+    oracle may part is the reference's SigErr fall-back (spline -> linint), whose verdict hangs on
+    the last bits of T and exp(): particles that have not met it on either
+    side must agree to 1e-9, and they are nearly all of them."""
+    rg, ro, res, ev, st, fg, fo, sg, so = _pair(2000, 1, nint=4, sigerr=True, **dict(PASSIVE, HTurbOn=1, VTurbOn=1))
     H = 30.0
     dz = np.abs(fg["z"] - fo["z"]) / H
+    clean = (sg == 0) & (so == 0)
+    assert clean.mean() >= 0.99 and dz[clean].max() <= 1e-9, (float(clean.mean()), float(dz[clean].max()))
+    assert np.array_equal(fg["r_ele"][clean], fo["r_ele"][clean])
     assert np.mean(dz <= 1e-9) >= 0.995, float(np.mean(dz <= 1e-9))
     assert np.median(dz) <= 1e-14
     assert dz.max() <= 1e-3
@@ -110,18 +112,24 @@ def test_vturb_same_stream_short_horizon():
 
 
 def test_vturb_long_horizon_distribution():
-    """60 internal steps of HTurb + VTurb: most particles still agree to 1e-9; the rest differ
-    only through chaotic amplification, so the depth distributions must coincide."""
+    """60 internal steps of HTurb + VTurb (full-size grid): particles without a SigErr fall-back on
+    either side still agree to 1e-9 after 3,600 random displacements each; the others differ by
+    the fall-back and its chaotic amplification, so the depth distributions must coincide."""
     from scipy import stats as ss
-    rg, ro, res, ev, st, fg, fo = _pair(4000, 2, **dict(PASSIVE, HTurbOn=1, VTurbOn=1))
+    rg, ro, res, ev, st, fg, fo, sg, so = _pair(4000, 2, sigerr=True, world_kw={}, **dict(PASSIVE, HTurbOn=1, VTurbOn=1))
     H = 30.0
     dz = np.abs(fg["z"] - fo["z"]) / H
+    clean = (sg == 0) & (so == 0)
+    assert clean.mean() >= 0.9 and dz[clean].max() <= 1e-9, (float(clean.mean()), float(dz[clean].max()))
     assert np.median(dz) <= 1e-12
-    assert np.mean(dz <= 1e-9) >= 0.97
+    assert np.mean(dz <= 1e-9) >= 0.9
     assert np.mean(fg["r_ele"] == fo["r_ele"]) >= 0.995
     assert ss.ks_2samp(fg["z"], fo["z"]).pvalue > 0.2
     assert abs(np.mean(fg["z"]) - np.mean(fo["z"])) <= 1e-3 * H
     assert np.array_equal(st[0][:3], st[1][:3]) or np.abs(st[0][:3] - st[1][:3]).max() <= 2
+    # fall-back rates: the oracle sweeps all 4 ws - 1 intervals of the VTurb spline, the device only
+    # the 32-knot window around the particle (DESIGN.md section 6), so it takes the branch less often
+    assert 0.3 <= sg.sum() / max(1, so.sum()) <= 1.3, (int(sg.sum()), int(so.sum()))
 
 
 @pytest.mark.parametrize("name", ["passive", "hturb_salttemp", "oyster4_settle", "tidal7"])
@@ -134,6 +142,72 @@ def test_golden_fixtures(name):
             assert np.allclose(got[k], want[k], rtol=0, atol=1e-9 * max(1.0, float(np.abs(want[k]).max()))), (name, k)
         else:
             assert np.array_equal(got[k], want[k]), (name, k)
+
+
+def _stepwise(n, nsteps, **kw):
+    """CUDA and oracle side by side, one internal step at a time; returns per step the relative
+    differences and the SigErr fall-back counts of both sides."""
+    from oracle.oracle import Oracle
+    w = World()
+    prm = make_params(w, n, **kw)
+    g, o = LtransLib(), Oracle()
+    setup(g, w, prm, n); setup(o, w, prm, n); o.set_threads(os.cpu_count() or 1)
+    L = float(max(np.ptp(w.x_r), np.ptp(w.y_r))); H = float(w.h.max())
+    out = []
+    for it in range(1, nsteps + 1):
+        g.step(1, it); o.step(1, it)
+        fg, fo = g.fetch(("x", "y", "z", "status", "r_ele")), o.fetch(("x", "y", "z", "status", "r_ele"))
+        d = np.maximum(np.maximum(np.abs(fg["x"] - fo["x"]), np.abs(fg["y"] - fo["y"])) / L, np.abs(fg["z"] - fo["z"]) / H)
+        out.append((d, g.fetch_sigerr(), o.fetch_sigerr(), fg, fo))
+    return out
+
+
+def test_config1_parity_until_first_sigerr():
+    """BASELINE configs[0] grid (130x130x20), 5,000 passive particles, 30 internal steps, compared
+    after EVERY step.  The reference replaces a water-column spline by linint when SIGS raises
+    SigErr; that verdict is decided by the last bits of T and of exp(), so
+    CUDA and oracle take the branch at the same RATE but not at the same steps.  Claim checked
+    here: a particle agrees within 1e-9 for as long as neither side has taken the branch, every
+    larger difference belongs to a particle that has, and the two rates agree."""
+    hist = _stepwise(5000, 30, **PASSIVE)
+    for it, (d, sg, so, fg, fo) in enumerate(hist, 1):
+        clean = (sg == 0) & (so == 0)
+        assert d[clean].max() <= 1e-9, (it, float(d[clean].max()))
+        assert np.array_equal(fg["status"], fo["status"]) and np.array_equal(fg["r_ele"][clean], fo["r_ele"][clean])
+    d, sg, so, fg, fo = hist[-1]
+    assert clean.mean() > 0.97                                   # ~4e-4 fall-backs per particle-step and side
+    assert d.max() <= 1e-5                                       # a fall-back moves a particle by ~1e-7 of the depth
+    ng, no = int(sg.sum()), int(so.sum())
+    assert 20 <= ng <= 120 and 20 <= no <= 120 and 0.5 <= ng / no <= 2.0, (ng, no)
+
+
+def test_config1_two_days_passive():
+    """BASELINE configs[0] at full size: 130x130x20 grid, 5,000 passive particles, RK4 advection
+    only, 2 days = 48 external x 30 internal steps (7.2e6 particle-steps), CUDA vs oracle.  Over
+    1,440 steps most particles meet a SigErr fall-back on one side or the other (see the test
+    above); the ones that never do must agree to 1e-9, all of them to 1e-4 of the domain, and
+    statuses / boundary events must be identical."""
+    from oracle.oracle import Oracle
+    w = World(); n = 5000
+    prm = make_params(w, n, **PASSIVE)
+    g, o = LtransLib(), Oracle()
+    setup(g, w, prm, n); setup(o, w, prm, n); o.set_threads(os.cpu_count() or 1)
+    rg, ro = run(g, w, 48), run(o, w, 48)
+    fg, fo = g.fetch(), o.fetch()
+    sg, so = g.fetch_sigerr(), o.fetch_sigerr()
+    stg, sto = g.stats(), o.stats()
+    assert rg == ro and g.drain_events() == o.drain_events()
+    assert np.array_equal(stg[[0, 1, 2, 5, 6, 7]], sto[[0, 1, 2, 5, 6, 7]]), (stg, sto)      # settled, dead, out, errors, active, unborn
+    assert np.all(np.abs(stg[3:5] - sto[3:5]) <= 0.002 * sto[3:5] + 2), (stg, sto)            # land / bottom hit totals
+    assert np.array_equal(fg["status"], fo["status"]) and np.array_equal(fg["age"], fo["age"])
+    L = float(max(np.ptp(w.x_r), np.ptp(w.y_r))); H = float(w.h.max())
+    d = np.maximum(np.maximum(np.abs(fg["x"] - fo["x"]), np.abs(fg["y"] - fo["y"])) / L, np.abs(fg["z"] - fo["z"]) / H)
+    clean = (sg == 0) & (so == 0)
+    assert clean.sum() >= 0.2 * n and d[clean].max() <= 1e-9, (int(clean.sum()), float(d[clean].max()))
+    assert np.array_equal(fg["r_ele"][clean], fo["r_ele"][clean])
+    assert np.median(d) <= 1e-9 and np.quantile(d, 0.99) <= 1e-5, (float(np.median(d)), float(np.quantile(d, 0.99)))
+    assert (fg["r_ele"] != fo["r_ele"]).mean() <= 0.002
+    assert 0.6 <= sg.sum() / so.sum() <= 1.6, (int(sg.sum()), int(so.sum()))
 
 
 def test_full_size_properties():

@@ -13,7 +13,7 @@ recs = [w.record(k) for k in range(12)]
 for k in range(3): g.push_hydro(recs[k])
 dbg = getattr(g.lib, "ltgpu_debug_counters", None) if hasattr(g, "lib") else None
 g.kernel_times(True)
-for p in range(1, 6):
+for p in range(1, 5):
     if p > 2: g.push_hydro(recs[p]); g.rotate_hydro()
     g.run_external(p); ms, st = g.kernel_times(True)
     extra = ""
