@@ -429,16 +429,20 @@ LT_DEV bool newton_step(NewtonState& q, double& out, int& err)
         double SINHM, COSHM, COSHMM;
         snhcsh(SIG, SINHM, COSHM, COSHMM);
         double RS_ = qrcp(SINHM);
-        T1 = COSHM * RS_;
+        T1 = qdiv(COSHM, SINHM);
         FP = T1 + SIG * (SIG * RS_ - T1 * T1 + 1.0);
     } else {
+        // products and sums rounded separately (no FMA contraction): the rounding noise of SSM
+        // and F decides how often the loop wanders instead of converging, and the fall-back
+        // RATE has to be the reference's
         double EMS = exp_neg(-SIG);
-        double SSM = 1.0 - EMS * (EMS + SIG + SIG);
+        double SSM = __dsub_rn(1.0, __dmul_rn(EMS, (EMS + SIG + SIG)));
+        double OM = 1.0 - EMS;
+        T1 = qdiv(__dmul_rn(OM, OM), SSM);
         double RM_ = qrcp(SSM);
-        T1 = (1.0 - EMS) * (1.0 - EMS) * RM_;
         FP = T1 + SIG * (2.0 * SIG * EMS * RM_ - T1 * T1 + 1.0);
     }
-    double F = SIG * T1 - q.TP1;
+    double F = __dsub_rn(__dmul_rn(SIG, T1), q.TP1);
     if (++q.NIT > 10000) { LT_DBG_COUNT(0); err = 1; out = 0.0; return true; }         // tension:556-559
     if (FP <= 0.0) { out = fmin(SIG, SBIG); return true; }
     double DSIG = -qdiv(F, FP);

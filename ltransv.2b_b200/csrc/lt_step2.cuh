@@ -663,6 +663,62 @@ struct VtCtx {
             }
         }
     }
+    // Optional (ltgpu_params.vturb_full_sigs): the reference's SIGS sweeps all p2 - 1 intervals of
+    // the fit and any SigErr sends the whole particle-step to linint (ver_turb:278-279, 300-336),
+    // the window above only sees its own intervals.  This pass streams over every knot (values,
+    // YPC1 slopes, T), keeps nothing, and runs the Newton loop for the intervals whose T lies in
+    // the band where it can fail (LT_BAND_*), so that `sigerr` is the reference's verdict.
+    LT_DEVN void sweep()
+    {
+        double S[3] = {0.0, 0.0, 0.0}; Seg hi[3], lo[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            seg_load(hi[t], t, 1); lo[t] = hi[t];
+            double acc = 0.0;
+            for (int j = 2; j <= 9; ++j) acc += newy(t, j, hi[t]);
+            S[t] = acc;
+            double d = newy(t, 2, lo[t]); (void)d;
+        }
+        double fm2 = 0.0, fm1 = 0.0, f0 = 0.0, ypm2 = 0.0;
+        int np = 0;
+        auto flush = [&]() {
+            for (int c = 0; c < np; ++c) {
+                NewtonState ns; newton_start(ns, tp[c] + 1.0, sig_guess(tp[c]));
+                double o; int e = 0;
+                while (!newton_step(ns, o, e)) {}
+                if (e) sigerr = true;
+            }
+            np = 0;
+        };
+        for (int k = 1; k <= p2; ++k) {
+            double my[3];
+            if (k == 1) { my[0] = khp[0][0]; my[1] = khp[1][0]; my[2] = khp[2][0]; }
+            else if (k == p2) { my[0] = khp[0][ws - 1]; my[1] = khp[1][ws - 1]; my[2] = khp[2][ws - 1]; }
+            else {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (k > 2) S[t] += newy(t, k + 7, hi[t]) - newy(t, k - 1, lo[t]);
+                    my[t] = S[t] / 8.0;
+                }
+            }
+            double fb = lag(D.LW[0], my[0], my[1], my[2]), fc = lag(D.LW[1], my[0], my[1], my[2]), ff = lag(D.LW[2], my[0], my[1], my[2]);
+            fb = fb < 0.0 ? 0.0 : fb; fc = fc < 0.0 ? 0.0 : fc; ff = ff < 0.0 ? 0.0 : ff;
+            fm2 = fm1; fm1 = f0; f0 = (fb + 4.0 * fc + ff) / 6.0;          // fy(k-2), fy(k-1), fy(k)
+            if (k < 3) continue;
+            const double d1 = knot_x(k - 1) - knot_x(k - 2), d2 = knot_x(k) - knot_x(k - 1);
+            const double s1 = qdiv(fm1 - fm2, d1), s2 = qdiv(f0 - fm1, d2);
+            const double ypk1 = ypc1_mid(d1, d2, s1, s2);                  // slope at knot k-1
+            if (k == 3) ypm2 = ypc1_end(s1, s1 + qdiv(d1 * (s1 - s2), d1 + d2));       // slope at knot 1
+            double Tq;
+            if (sigerr_candidate(s1, ypm2, ypk1, Tq)) { tp[np++] = Tq; if (np == VW) flush(); }   // interval (k-2, k-1)
+            ypm2 = ypk1;
+            if (k == p2) {
+                const double ypN = ypc1_end(s2, s2 + qdiv(d2 * (s2 - s1), d1 + d2));
+                if (sigerr_candidate(s2, ypk1, ypN, Tq)) { tp[np++] = Tq; if (np == VW) flush(); }   // interval (p2-1, p2)
+            }
+        }
+        flush();
+    }
     // HVAL / HPVAL interval choice incl. INTRVL (tension:1026-1041, 1287-1354)
     LT_DEV int interval(double Tq) const
     {
@@ -703,6 +759,7 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     V.ZN = lag(D.LW4, V.zl[0][V.ws - 1], V.zl[1][V.ws - 1], V.zl[2][V.ws - 1]);
     V.H = (V.ZN - V.Z1) * rp2; V.rH = qrcp(V.H);
     V.ka = 1; V.kb = 0; V.ia = 1; V.ib = 0;
+    if (D.P.vturb_full_sigs) V.sweep();
     const Rng g = make_rng(D, n);
     const double deltat = 2.0;
     const int loop = D.P.idt / 2;                                       // :282-283

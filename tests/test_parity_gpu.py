@@ -132,6 +132,23 @@ def test_vturb_long_horizon_distribution():
     assert 0.3 <= sg.sum() / max(1, so.sum()) <= 1.3, (int(sg.sum()), int(so.sum()))
 
 
+def test_vturb_full_sigs_option_matches_reference_rate():
+    """ltgpu_params.vturb_full_sigs = 1: the VTurb fit is swept over all 4 ws - 1 intervals for
+    SigErr like the reference (ver_turb:278-279), so the fall-back RATE equals the oracle's; with
+    the default (window only) the device takes the branch less often."""
+    n = 6000
+    out = {}
+    for full in (0, 1):
+        rg, ro, res, ev, st, fg, fo, sg, so = _pair(n, 1, sigerr=True, world_kw={}, **dict(PASSIVE, HTurbOn=1, VTurbOn=1, vturb_full_sigs=full))
+        dz = np.abs(fg["z"] - fo["z"]) / 30.0
+        clean = (sg == 0) & (so == 0)
+        assert dz[clean].max() <= 1e-9 and clean.mean() > 0.95
+        out[full] = (int(sg.sum()), int(so.sum()))
+    assert out[0][1] == out[1][1]                               # the oracle ignores the switch
+    assert 0.7 <= out[1][0] / out[1][1] <= 1.4, out             # ~110 events: +-10 % is one sigma
+    assert out[0][0] < out[1][0], out
+
+
 @pytest.mark.parametrize("name", ["passive", "hturb_salttemp", "oyster4_settle", "tidal7"])
 def test_golden_fixtures(name):
     from golden.make_golden import run_case
