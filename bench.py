@@ -190,15 +190,6 @@ def main():
         if fetch:
             return g.fetch(("x", "y", "z", "status"))
 
-    # bring the GPU to its load clocks before the warm-up steps (some GPUs of a node needed
-    # ~1 s of load before their step time settled; untimed, does not touch the particle state)
-    a_ = torch.randn(4096, 4096, device="cuda")
-    t_ = time.perf_counter()
-    while time.perf_counter() - t_ < 1.5:
-        for _ in range(20):
-            a_ = torch.tanh(a_ @ a_ * 1e-3)
-        torch.cuda.synchronize()
-    del a_
     # p = 1, 2 run on the initial three records (no updateHydro before the 3rd external step)
     for _ in range(args.warmup):
         one_step(False)
