@@ -221,6 +221,14 @@ int32_t ltgpu_fetch(ltgpu_ctx* ctx,
     double* salt, double* temp, int32_t* hitBottom, int32_t* hitLand,
     int32_t* endpoly, double* lifespan,
     int32_t* r_ele, int32_t* u_ele, int32_t* v_ele);
+/* Particle positions as longitude / latitude for the writers: x2lon(x, y) and y2lat(y) of
+ * conversion_module.f90:322-378 (double-precision branches; `spherical` = SphericalProjection,
+ * lonmin / latmin as stored by CONVERT_MOD, i.e. the namelist values minus 1,
+ * parameter_module.f90:133-134; PI from ltgpu_params).  Saves the host its per-particle
+ * conversion loop of writeOutput (LTRANS.f90:1712-1716). */
+int32_t ltgpu_fetch_lonlat(ltgpu_ctx* ctx, int32_t spherical, double lonmin, double latmin,
+                           double earth_radius, double* lon, double* lat);
+
 /* Diagnostic (no reference counterpart): how many times each particle's water-column
  * profile fell back from the tension spline to linint because SIGS raised SigErr
  * (hydro:2621-2644, ver_turb:300-336).  The reference takes that branch silently; its

@@ -211,6 +211,22 @@ __global__ void k_screen(const LtDev D, unsigned long long* __restrict__ cnt)
     atomicAdd(cnt + (code - LTGPU_EV_INIT_OUT_MAIN), 1ull);
 }
 
+// x2lon / y2lat, double-precision branches (conversion_module.f90:322-378), per slot
+__global__ void k_lonlat(const LtDev D, int spherical, double lonmin, double latmin, double R, double* __restrict__ lon, double* __restrict__ lat)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= D.n) return;
+    const double pi = D.P.PI, RCF = 180.0 / pi, x = D.x[n], y = D.y[n];
+    if (spherical) {
+        double la = y * 180.0 / (R * pi) + latmin;
+        lon[n] = x * 180.0 / (R * pi * cos(la / RCF)) + lonmin;
+        lat[n] = y * RCF / R + latmin;
+    } else {
+        lon[n] = x / R * RCF;
+        lat[n] = 2.0 * RCF * (atan(exp(y / R)) - pi / 4.0);
+    }
+}
+
 __global__ void k_fill_i32(int* p, int v, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -954,6 +970,20 @@ int32_t ltgpu_fetch(ltgpu_ctx* ctx, double* x, double* y, double* z, double* age
     TRY(fetch_col(ctx, endpoly, (const int*)D.endpoly)); TRY(fetch_col(ctx, lifespan, (const double*)D.lifespan));
     TRY(fetch_col(ctx, r_ele, (const int*)D.r_ele)); TRY(fetch_col(ctx, u_ele, (const int*)D.u_ele)); TRY(fetch_col(ctx, v_ele, (const int*)D.v_ele));
     (void)N; (void)s;
+    return fetch_flush(ctx);
+}
+
+int32_t ltgpu_fetch_lonlat(ltgpu_ctx* ctx, int32_t spherical, double lonmin, double latmin, double earth_radius, double* lon, double* lat)
+{
+    if (!ctx || !lon || !lat) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "fetch_lonlat before set_particles");
+    ARG(earth_radius > 0.0, "fetch_lonlat: bad earth radius");
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D;
+    // s_nx / s_ny are per-slot scratch of the step kernels, rewritten by k_advect before they are read
+    k_lonlat<<<(D.n + 255) / 256, 256, 0, ctx->compute>>>(D, spherical, lonmin, latmin, earth_radius, D.s_nx, D.s_ny);
+    ctx->launches++;
+    TRY(fetch_col(ctx, lon, (const double*)D.s_nx)); TRY(fetch_col(ctx, lat, (const double*)D.s_ny));
     return fetch_flush(ctx);
 }
 

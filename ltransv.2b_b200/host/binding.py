@@ -243,6 +243,14 @@ class LtransLib:
         self._check(rc, "fetch")
         return {k: v for k, v in out.items() if v is not None}
 
+    def fetch_lonlat(self, proj, spherical=True):
+        """(lon, lat) of every particle, converted on the device (x2lon / y2lat)"""
+        lon, lat = np.zeros(self.n), np.zeros(self.n)
+        rc = self._fn("fetch_lonlat")(self.ctx, C.c_int32(1 if spherical else 0), C.c_double(proj.lonmin), C.c_double(proj.latmin),
+                                      C.c_double(proj.R), _p(lon), _p(lat))
+        self._check(rc, "fetch_lonlat")
+        return lon, lat
+
     def fetch_sigerr(self):
         """diagnostic: SigErr (linint) fall-backs per particle so far"""
         c = np.zeros(self.n, dtype=np.int32)

@@ -88,9 +88,8 @@ class Run:
     # printOutput / writeOutput (:1617-1779)
     def print_output(self, ix3):
         self.prcount += 1
-        f = self.e.fetch(("x", "y", "z", "age", "status", "salt", "temp", "hitBottom", "hitLand"))
-        P = self.w.proj
-        lon, lat = P.x2lon(f["x"], f["y"]), P.y2lat(f["y"])
+        f = self.e.fetch(("z", "age", "status", "salt", "temp", "hitBottom", "hitLand"))
+        lon, lat = self.e.fetch_lonlat(self.w.proj)             # :1712-1716 x2lon / y2lat, on the device
         if self.write_csv:
             st = self.prm.SaltTempOn
             formats.write_para_csv(formats.para_filename(self.prcount, self.outdir), f["z"], f["status"], lon, lat,
@@ -108,8 +107,7 @@ class Run:
     # fin_LTRANS (:618-658)
     def finish(self):
         f = self.e.fetch(("x", "y", "status", "endpoly", "lifespan"))
-        P = self.w.proj
-        lon, lat = P.x2lon(f["x"], f["y"]), P.y2lat(f["y"])
+        lon, lat = self.e.fetch_lonlat(self.w.proj)
         if self.write_csv:
             sp = self.startpoly if self.prm.settlementon else None
             if self.prm.settlementon and sp is None:

@@ -73,6 +73,7 @@ int32_t ora_rotate_hydro(ora_ctx* c);
 int32_t ora_step(ora_ctx* c, int32_t p, int32_t it);
 int32_t ora_run_external(ora_ctx* c, int32_t p);
 int32_t ora_screen_initial(ora_ctx* c, int64_t counts[5], int64_t* bad_particle);
+int32_t ora_fetch_lonlat(ora_ctx* c, int32_t spherical, double lonmin, double latmin, double earth_radius, double* lon, double* lat);
 int32_t ora_fetch_sigerr(ora_ctx* c, int32_t* count);
 int32_t ora_sync(ora_ctx* c, int32_t* bad_particle);
 

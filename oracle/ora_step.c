@@ -1353,6 +1353,24 @@ int32_t ora_screen_initial(ora_ctx* c, int64_t counts[5], int64_t* bad_particle)
     return LTGPU_OK;
 }
 
+/* conversion_module.f90:322-378, double-precision branches */
+int32_t ora_fetch_lonlat(ora_ctx* c, int32_t spherical, double lonmin, double latmin, double earth_radius, double* lon, double* lat)
+{
+    const double pi = c->prm.PI, RCF = 180.0 / pi, R = earth_radius;
+    for (int n = 0; n < c->n; ++n) {
+        double x = c->X[n], y = c->Y[n];
+        if (spherical) {
+            double la = y * 180.0 / (R * pi) + latmin;
+            lon[n] = x * 180.0 / (R * pi * cos(la / RCF)) + lonmin;
+            lat[n] = y * RCF / R + latmin;
+        } else {
+            lon[n] = x / R * RCF;
+            lat[n] = 2.0 * RCF * (atan(exp(y / R)) - pi / 4.0);
+        }
+    }
+    return LTGPU_OK;
+}
+
 int32_t ora_fetch_sigerr(ora_ctx* c, int32_t* count)
 {
     memcpy(count, c->nsig, sizeof(int32_t) * (size_t)c->n);

@@ -105,3 +105,19 @@ def test_run_loop_from_netcdf_files(tmp_path):
         assert np.array_equal(f.variables["color"][-1], last[:, 1])
         assert np.allclose(f.variables["lon"][-1], last[:, 2], rtol=0, atol=5.01e-5)
         assert np.allclose(f.variables["salinity"][-1], last[:, 4], rtol=0, atol=5.01e-5)
+
+
+def test_lonlat_conversion_matches_projection():
+    """ora_fetch_lonlat / ltgpu_fetch_lonlat = x2lon, y2lat of conversion_module.f90:322-378"""
+    from oracle.oracle import Oracle
+    w = World(**SMALL); n = 500
+    prm = make_params(w, n, Behavior=0, settlementon=0)
+    o = Oracle(); o.create(prm); o.set_grid(w.grid()); o.set_bounds(w.bounds())
+    x, y, z, dob, r, u, v = w.seed_particles(n, seed=3)
+    o.set_particles(x, y, z, dob, None, r, u, v)
+    lon, lat = o.fetch_lonlat(w.proj)
+    assert np.allclose(lon, w.proj.x2lon(x, y), rtol=0, atol=1e-12) and np.allclose(lat, w.proj.y2lat(y), rtol=0, atol=1e-12)
+    assert np.allclose(w.proj.lon2x(lon, lat), x, rtol=1e-12) and np.allclose(w.proj.lat2y(lat), y, rtol=1e-12)
+    lon_m, lat_m = o.fetch_lonlat(w.proj, spherical=False)       # Mercator branch
+    R, pi = w.proj.R, w.proj.pi
+    assert np.allclose(lon_m, x / R * 180.0 / pi, rtol=1e-14) and np.allclose(lat_m, 2 * 180.0 / pi * (np.arctan(np.exp(y / R)) - pi / 4), rtol=1e-12, atol=1e-12)

@@ -336,6 +336,20 @@ def test_oyster_run_with_turbulence_statistics():
     assert np.mean(np.abs(fg["x"] - fo["x"]) <= 1e-6 * 1.4e4) >= 0.95
 
 
+def test_lonlat_on_device():
+    from oracle.oracle import Oracle
+    w = World(**SMALL); n = 3000
+    prm = make_params(w, n, **PASSIVE)
+    g, o = LtransLib(), Oracle()
+    setup(g, w, prm, n); setup(o, w, prm, n)
+    run(g, w, 1); run(o, w, 1)
+    for sph in (True, False):
+        a, b = g.fetch_lonlat(w.proj, spherical=sph), o.fetch_lonlat(w.proj, spherical=sph)
+        assert np.allclose(a[0], b[0], rtol=0, atol=1e-11) and np.allclose(a[1], b[1], rtol=0, atol=1e-11)
+    f = g.fetch(("x", "y"))
+    assert np.allclose(a[0], f["x"] / w.proj.R * 180.0 / w.proj.pi, rtol=1e-13)
+
+
 def test_abi_misc_calls():
     """reset_hits, stats, device_ptr (particle-order copies), kernel_times, launch_count."""
     import ctypes as C
