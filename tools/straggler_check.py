@@ -20,4 +20,4 @@ for p in range(1, 5):
     if dbg:
         c = (ctypes.c_ulonglong * 88)(); dbg(g.ctx, c, 1); print("   up", list(c)[24:56]); print("   dn", list(c)[56:88]); extra = "  census " + str(list(c)[:7]) + " build " + str(list(c)[16:20])
         if c[3]: extra += "\n   case " + " ".join(np.array(list(c)[8:], np.uint64).view(np.float64).astype(float).__iter__().__class__ and [float.hex(float(v)) for v in np.array(list(c)[8:], np.uint64).view(np.float64)])
-    print("p=%d  advect %.1f  vturb %.1f  finish %.1f  (ms per external step)%s" % (p, ms[0], ms[1], ms[2], extra))
+    print("p=%d  advect %.1f  vturb %.1f (walk %.1f)  finish %.1f  (ms per external step)%s" % (p, ms[0], ms[1], ms[3], ms[2], extra))
