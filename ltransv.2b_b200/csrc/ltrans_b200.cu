@@ -87,15 +87,20 @@ __global__ void k_fill_slot(const TI* __restrict__ in, const uint8_t* __restrict
     }
 }
 
-// ---- periodic re-sort of the particle slots by (depth bin, rho element) -------------------
+// ---- re-sort of the particle slots by (depth bin, rho element), every internal step ---------
 // Particles never interact, so slot order is free.  What pays in this FP64 code is lanes that
-// take the same branches: spline interval and tension regime, level walks of the VTurb fit,
-// Newton iteration counts.  Those follow the particle's relative depth, so the depth bin is the
-// MAJOR key (16 bins of the local water column) and the rho element the minor one; within a bin
-// neighbouring lanes still sit in neighbouring elements, which keeps the stencil gathers local.
-// Measured against the element-major key (re << 3 | depth octile, LTGPU_SORT_MODE=0): -4 % of
-// the step on the 130x130x20 benchmark, -20 % at Gulf scale (ws = 37), where `k_vturb` drops
-// from 64 to 42 ms per internal step for 12.5 M particles.
+// take the same branches: level window and log-layer test of find_currents, spline interval and
+// tension regime, level walks of the VTurb fit, Newton iteration counts.  Those follow the
+// particle's relative depth, so the depth bin is the MAJOR key (32 bins of the local water
+// column) and the rho element the minor one; within a bin neighbouring lanes still sit in
+// neighbouring elements, which keeps the stencil gathers local.  Vertical turbulence scrambles
+// the bins within a few internal steps, so the sort runs before every step: key build, CUB
+// radix sort of (key, slot) and ONE kernel that moves all 21 state columns (122 B per particle)
+// cost 0.07 ms per step at 1 M particles.  Measured on the 130x130x20 benchmark (particle-steps/s):
+// element-major key once per external step 128 M; depth-major once per external step 132 M,
+// every 10 / 5 / 2 / 1 steps 141 / 146 / 153 / 157 M; 32 bins and the fused move 163 M.  At Gulf
+// scale (ws = 37, 12.5 M particles) depth-major takes `k_vturb` from 64 to 41 ms per step.
+// LTGPU_SORT=0 disables, LTGPU_SORT_MODE=<bins> (0 = element-major), LTGPU_SORT_EVERY=<steps>.
 __global__ void k_sort_keys(const LtDev D, unsigned* __restrict__ key, int* __restrict__ idx, int bins)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,10 +273,11 @@ struct ltgpu_ctx {
     bool have_grid = false, have_bounds = false, have_particles = false, have_habitat = false;
     int nthreads_grid = 0;
     // re-sort state
-    bool sort_on = true; int sort_mode = 16, sort_every = 1 << 30;
+    bool sort_on = true; int sort_mode = 32, sort_every = 1;
     unsigned *d_key = nullptr, *d_key2 = nullptr; int *d_idx = nullptr, *d_perm = nullptr, *d_pid = nullptr;
     void* d_cub = nullptr; size_t cub_bytes = 0;
-    double* spare8 = nullptr; int* spare4 = nullptr; uint8_t* spare1 = nullptr; double* out8 = nullptr;
+    double* spare8 = nullptr; double* out8 = nullptr;          // bounce buffers of ltgpu_fetch
+    double* alt8[11] = {}; int* alt4[8] = {}; uint8_t* alt1[2] = {};   // second copy of the per-slot state (re-sort target)
     void* h_out[2] = {nullptr, nullptr};     // pinned bounce buffers for fetch (pageable D2H is 4-5x slower)
     cudaEvent_t out_done[2] = {nullptr, nullptr}; int out_i = 0;
     void* pend_host[2] = {nullptr, nullptr}; size_t pend_bytes[2] = {0, 0};
@@ -448,27 +454,43 @@ static int32_t build_indices(ltgpu_ctx* ctx, const std::vector<double4>& seg, co
 }
 
 // ---------------------------------------------------------------- re-sort ----
-template <class V>
-static void permute(ltgpu_ctx* ctx, V** arr, V** spare)
+// all per-slot state in one pass: slot i takes the state of old slot perm[i]
+#define LT_NP8 11
+#define LT_NP4 8
+#define LT_NP1 2
+struct PermArgs { const double* s8[LT_NP8]; double* d8[LT_NP8]; const int* s4[LT_NP4]; int* d4[LT_NP4]; const uint8_t* s1[LT_NP1]; uint8_t* d1[LT_NP1]; };
+__global__ void k_permute_all(const __grid_constant__ PermArgs a, const int* __restrict__ perm, int n)
 {
-    int n = ctx->D.n;
-    k_gather<V><<<(n + 255) / 256, 256, 0, ctx->compute>>>(*arr, *spare, ctx->d_perm, n);
-    std::swap(*arr, *spare);
-    ctx->launches++;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = perm[i];
+#pragma unroll
+    for (int k = 0; k < LT_NP8; ++k) a.d8[k][i] = a.s8[k][j];
+#pragma unroll
+    for (int k = 0; k < LT_NP4; ++k) a.d4[k][i] = a.s4[k][j];
+#pragma unroll
+    for (int k = 0; k < LT_NP1; ++k) a.d1[k][i] = a.s1[k][j];
 }
 static int32_t resort(ltgpu_ctx* ctx)
 {
     LtDev& D = ctx->D; int n = D.n;
     k_sort_keys<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_key, ctx->d_idx, ctx->sort_mode);
     CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_perm, n, 0, ctx->key_bits, ctx->compute));
-    ctx->launches += 2;
-    double** a8[] = {&D.x, &D.y, &D.z, &D.age, &D.dob, &D.lifespan, &D.psalt, &D.ptemp, &D.timer, &D.sprev, &D.zprev};
-    for (auto p : a8) permute(ctx, p, &ctx->spare8);
-    int** a4[] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly, &D.nsig, &ctx->d_pid};
-    for (auto p : a4) permute(ctx, p, &ctx->spare4);
-    permute(ctx, &D.flags, &ctx->spare1);
-    { uint8_t* b = (uint8_t*)D.behave; permute(ctx, &b, &ctx->spare1); D.behave = (int8_t*)b; }
+    double** a8[LT_NP8] = {&D.x, &D.y, &D.z, &D.age, &D.dob, &D.lifespan, &D.psalt, &D.ptemp, &D.timer, &D.sprev, &D.zprev};
+    int** a4[LT_NP4] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly, &D.nsig, &ctx->d_pid};
+    uint8_t* beh = (uint8_t*)D.behave;
+    uint8_t** a1[LT_NP1] = {&D.flags, &beh};
+    PermArgs pa;
+    for (int k = 0; k < LT_NP8; ++k) { pa.s8[k] = *a8[k]; pa.d8[k] = ctx->alt8[k]; }
+    for (int k = 0; k < LT_NP4; ++k) { pa.s4[k] = *a4[k]; pa.d4[k] = ctx->alt4[k]; }
+    for (int k = 0; k < LT_NP1; ++k) { pa.s1[k] = *a1[k]; pa.d1[k] = ctx->alt1[k]; }
+    k_permute_all<<<(n + 255) / 256, 256, 0, ctx->compute>>>(pa, ctx->d_perm, n);
+    for (int k = 0; k < LT_NP8; ++k) std::swap(*a8[k], ctx->alt8[k]);
+    for (int k = 0; k < LT_NP4; ++k) std::swap(*a4[k], ctx->alt4[k]);
+    for (int k = 0; k < LT_NP1; ++k) std::swap(*a1[k], ctx->alt1[k]);
+    D.behave = (int8_t*)beh;
     D.pid = ctx->d_pid;
+    ctx->launches += 3;
     CK(cudaGetLastError());
     ctx->sorts++;
     return LTGPU_OK;
@@ -546,7 +568,7 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     const char* so = getenv("LTGPU_SORT");
     ctx->sort_on = !(so && so[0] == '0');
     { const char* se = getenv("LTGPU_SORT_EVERY"); if (se && atoi(se) > 0) ctx->sort_every = atoi(se); }
-    { const char* sm = getenv("LTGPU_SORT_MODE"); ctx->sort_mode = sm ? std::max(0, std::min(127, atoi(sm))) : 16; }
+    { const char* sm = getenv("LTGPU_SORT_MODE"); ctx->sort_mode = sm ? std::max(0, std::min(127, atoi(sm))) : 32; }
     *out = ctx;
     return LTGPU_OK;
 }
@@ -794,7 +816,10 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
     TRY(dalloc(ctx, &D.s_act, N));
     TRY(dalloc(ctx, &ctx->d_pid, N)); TRY(dalloc(ctx, &ctx->d_perm, N)); TRY(dalloc(ctx, &ctx->d_idx, N));
     TRY(dalloc(ctx, &ctx->d_key, N)); TRY(dalloc(ctx, &ctx->d_key2, N));
-    TRY(dalloc(ctx, &ctx->spare8, N)); TRY(dalloc(ctx, &ctx->spare4, N)); TRY(dalloc(ctx, &ctx->spare1, N)); TRY(dalloc(ctx, &ctx->out8, N));
+    TRY(dalloc(ctx, &ctx->spare8, N)); TRY(dalloc(ctx, &ctx->out8, N));
+    for (auto& q : ctx->alt8) TRY(dalloc(ctx, &q, N));
+    for (auto& q : ctx->alt4) TRY(dalloc(ctx, &q, N));
+    for (auto& q : ctx->alt1) TRY(dalloc(ctx, &q, N));
     for (int b = 0; b < 2; ++b) {          // pinned bounce buffers of ltgpu_fetch (allocated here: cudaMallocHost is slow)
         CK(cudaMallocHost(&ctx->h_out[b], sizeof(double) * N));
         CK(cudaEventCreateWithFlags(&ctx->out_done[b], cudaEventDisableTiming));
