@@ -29,8 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-TRAFFIC_BYTES_PER_STEP = 4.80e9  # dram read+write bytes of the 3 kernels per internal step per 1e6 particles
-                                 # (ncu --set full, profiles/r01h_ncu_summary.csv)
+TRAFFIC_BYTES_PER_STEP = 4.94e9  # dram read+write bytes of the 3 kernels per internal step per 1e6 particles
+                                 # (ncu --set full, profiles/r01i_ncu_summary.csv)
 B_ALG = 3624          # algorithmic bytes / particle-step, config 2
 NPART = 1_000_000
 WORKLOAD = "baymouth-shape 130x130x20 synthetic ROMS, 1M particles/GPU, HTurb+VTurb, 30 internal steps per step"
