@@ -730,6 +730,24 @@ struct VtCtx {
         while (k < p2 - 1 && !(Tq < knot_x(k + 1))) ++k;
         return k;
     }
+    // the same choice, also returning the interval's end knots (the walk needs them anyway, so
+    // the common case costs two knot_x instead of four)
+    LT_DEV int interval_x(double Tq, double& X1, double& X2) const
+    {
+        int k;
+        if (Tq < Z1) k = 1;
+        else if (Tq > ZN) k = p2 - 1;
+        else {
+            k = (int)floor((Tq - Z1) * rH + 0.5);
+            k = max(1, min(p2 - 1, k));
+            X1 = knot_x(k); X2 = knot_x(k + 1);
+            while (k > 1 && Tq < X1) { --k; X2 = X1; X1 = knot_x(k); }
+            while (k < p2 - 1 && !(Tq < X2)) { ++k; X1 = X2; X2 = knot_x(k + 1); }
+            return k;
+        }
+        X1 = knot_x(k); X2 = knot_x(k + 1);
+        return k;
+    }
     LT_DEV void need(int I) { if (I < ia || I > ib) build(max(1, min(I - VW / 2 + 1, p2 - VW + 1))); }
 };
 
@@ -774,10 +792,10 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
 #endif
     auto load_iv = [&](double zq) {
         if (cI >= 0 && zq >= cX1 && zq < cX2) return;                  // still inside [X(I), X(I+1)): INTRVL gives I
-        int I = V.interval(zq); V.need(I);
+        int I = V.interval_x(zq, cX1, cX2); V.need(I);
         int q = I - V.ka;
         LT_ASSERT(I >= V.ia && I <= V.ib && q >= 0 && q + 1 < VW && I >= 1 && I <= V.p2 - 1);
-        cI = I; cX1 = V.knot_x(I); cX2 = V.knot_x(I + 1);
+        cI = I;
 #ifdef LT_DEBUG_TRACE
         if (dI0 < 0) dI0 = I; dImin = min(dImin, I); dImax = max(dImax, I);
 #endif
