@@ -121,3 +121,32 @@ def test_lonlat_conversion_matches_projection():
     lon_m, lat_m = o.fetch_lonlat(w.proj, spherical=False)       # Mercator branch
     R, pi = w.proj.R, w.proj.pi
     assert np.allclose(lon_m, x / R * 180.0 / pi, rtol=1e-14) and np.allclose(lat_m, 2 * 180.0 / pi * (np.arctan(np.exp(y / R)) - pi / 4), rtol=1e-12, atol=1e-12)
+
+
+def test_reference_case_round_trip(tmp_path):
+    """tools/make_reference_case.py writes a full LTRANS v.2b input set (LTRANS.data, grid and history
+    NetCDF, particle CSV); tools/run_case.py runs it from those files.  Same para files as a run fed
+    from memory with the positions read back from the CSV."""
+    import importlib.util
+    from oracle.oracle import Oracle
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+    mk, rc = load("make_reference_case"), load("run_case")
+    case = str(tmp_path / "case")
+    w = mk.make_case(case, n=80, days=0.125, small=True, tdim=3)
+    nml = formats.read_namelist(os.path.join(case, "LTRANS.data"))
+    prm, flat = formats.params_from_namelist(nml)
+    assert (prm.numpar, prm.us, prm.ws, prm.HTurbOn, prm.VTurbOn, prm.Behavior, prm.ErrorFlag) == (80, w.us, w.ws, 0, 0, 0, 1)
+    assert flat["readdens"] is False and flat["ncgridfile"] == "./input/grid.nc" and flat["tdim"] == 3
+    assert sorted(os.listdir(os.path.join(case, "input"))) == ["Initial_particle_locations.csv", "grid.nc", "his_0001.nc", "his_0002.nc"]
+    out = rc.run_case(case, engine="oracle")
+    lon, lat, z, dob, _ = formats.read_particles_csv(os.path.join(case, "input", "Initial_particle_locations.csv"), False)
+    mem = str(tmp_path / "mem")
+    run = Run(Oracle(), w, prm, mem, days=0.125, iprint=3600)
+    run.init(lon, lat, z, dob); run.run()
+    names = sorted(n for n in os.listdir(mem) if n.startswith("para"))
+    assert names == ["para1000000%d.csv" % k for k in (2, 3, 4)]
+    for n in names + ["endfile.csv"]:
+        assert open(os.path.join(mem, n)).read() == open(os.path.join(out, n)).read(), n
+    assert np.all(rc.compare(out, mem) == 0)
