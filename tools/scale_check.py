@@ -9,12 +9,23 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from common import World, LtransLib, make_params
 import torch
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 12_500_000
+# python tools/scale_check.py [particles] [gulf|oyster]
+#   gulf   (default) BASELINE configs[3]/[4] per-GPU share: 1024x768x36, buoyant Behavior 6, open boundary
+#   oyster BASELINE configs[2]: Chesapeake-scale 120x80x20, Behavior 4, 64 settlement polygons with holes, mortality
+which = sys.argv[2] if len(sys.argv) > 2 else "gulf"
+n = int(sys.argv[1]) if len(sys.argv) > 1 else (12_500_000 if which == "gulf" else 10_000_000)
 t0 = time.time()
-w = World(ni=1024, nj=768, us=36, hmin=50.0, hmax=3000.0, dlon=0.02, dlat=0.018, speed=0.9)
-prm = make_params(w, n, Behavior=6, sink=0.002, settlementon=0, mortality=0, TrackCollisions=0, ErrorFlag=3)
+if which == "gulf":
+    w = World(ni=1024, nj=768, us=36, hmin=50.0, hmax=3000.0, dlon=0.02, dlat=0.018, speed=0.9)
+    prm = make_params(w, n, Behavior=6, sink=0.002, settlementon=0, mortality=0, TrackCollisions=0, ErrorFlag=3)
+else:
+    w = World(ni=120, nj=80, us=20, dlon=0.02, dlat=0.018)
+    prm = make_params(w, n, Behavior=4, settlementon=1, holesExist=1, mortality=1, TrackCollisions=0, ErrorFlag=3,
+                      pediage=3600.0, deadage=3 * 3600.0)
 g = LtransLib().create(prm)
 g.set_grid(w.grid()); g.set_bounds(w.bounds())
+if prm.settlementon:
+    g.set_habitat(w.habitat(npoly=64))
 x, y, z, dob, r, u, v = w.seed_particles(n)
 t1 = time.time()
 g.set_particles(x, y, z, dob, None, None, None, None)             # located on the device (element buckets)
