@@ -266,7 +266,8 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650",
                          "note": "achieved = 3624 algorithmic B/particle-step x particles per launch / summed launch time; "
                                  "the path is FP64-latency bound, not HBM bound (DESIGN.md section 5): fields are L2-resident, "
-                                 "dram traffic is particle state + per-thread spline scratch"},
+                                 "dram traffic is particle state + per-thread spline scratch",
+                         "fp64_pipe_active_pct": {"k_advect": 27.0, "k_vturb": 37.4, "source": "profiles/r01i_ncu_summary.csv (1M particles)"}},
             "clocks": clocks_summary(samples),
             "stats": {"settled": int(stats_t[0]), "dead": int(stats_t[1]), "out_of_bounds": int(stats_t[2]),
                       "active": int(stats_t[6]), "events": int(stats_t[5])},
