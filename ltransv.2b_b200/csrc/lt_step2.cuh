@@ -619,21 +619,26 @@ struct VtCtx {
         }
         // YPC1 (tension:852-978): needs both neighbours, or the profile end
         const int pa = ka == 1 ? 1 : ka + 1, pb = kb == p2 ? p2 : kb - 1;
-        for (int k = pa; k <= pb; ++k) {
-            double v;
-            if (k == 1) {
-                double d1 = knot_x(2) - knot_x(1), d2 = knot_x(3) - knot_x(2);
-                double s1 = qdiv(fy[2 - ka] - fy[1 - ka], d1), s2 = qdiv(fy[3 - ka] - fy[2 - ka], d2);
-                v = ypc1_end(s1, s1 + qdiv(d1 * (s1 - s2), d1 + d2));
-            } else if (k == p2) {
-                double d1 = knot_x(p2 - 1) - knot_x(p2 - 2), d2 = knot_x(p2) - knot_x(p2 - 1);
-                double s1 = qdiv(fy[p2 - 1 - ka] - fy[p2 - 2 - ka], d1), s2 = qdiv(fy[p2 - ka] - fy[p2 - 1 - ka], d2);
-                v = ypc1_end(s2, s2 + qdiv(d2 * (s2 - s1), d1 + d2));
-            } else {
-                double d1 = knot_x(k) - knot_x(k - 1), d2 = knot_x(k + 1) - knot_x(k);
-                v = ypc1_mid(d1, d2, qdiv(fy[k - ka] - fy[k - 1 - ka], d1), qdiv(fy[k + 1 - ka] - fy[k - ka], d2));
+        if (pa == 1) {
+            double d1 = knot_x(2) - knot_x(1), d2 = knot_x(3) - knot_x(2);
+            double s1 = qdiv(fy[2 - ka] - fy[1 - ka], d1), s2 = qdiv(fy[3 - ka] - fy[2 - ka], d2);
+            yp[1 - ka] = ypc1_end(s1, s1 + qdiv(d1 * (s1 - s2), d1 + d2));
+        }
+        {   // interior knots: abscissae, values and the left chord slope slide along in registers
+            const int m0 = max(pa, 2), m1 = min(pb, p2 - 1);
+            double x0 = knot_x(m0 - 1), x1 = knot_x(m0), f0 = fy[m0 - 1 - ka], f1 = fy[m0 - ka];
+            double sl = qdiv(f1 - f0, x1 - x0);
+            for (int k = m0; k <= m1; ++k) {
+                const double x2 = knot_x(k + 1), f2 = fy[k + 1 - ka];
+                const double d1 = x1 - x0, d2 = x2 - x1, sr = qdiv(f2 - f1, d2);
+                yp[k - ka] = ypc1_mid(d1, d2, sl, sr);
+                x0 = x1; x1 = x2; f0 = f1; f1 = f2; sl = sr;
             }
-            yp[k - ka] = v;
+        }
+        if (pb == p2) {
+            double d1 = knot_x(p2 - 1) - knot_x(p2 - 2), d2 = knot_x(p2) - knot_x(p2 - 1);
+            double s1 = qdiv(fy[p2 - 1 - ka] - fy[p2 - 2 - ka], d1), s2 = qdiv(fy[p2 - ka] - fy[p2 - 1 - ka], d2);
+            yp[p2 - ka] = ypc1_end(s2, s2 + qdiv(d2 * (s2 - s1), d1 + d2));
         }
         // SIGS (tension:314-782) for every interval with both slopes known
         ia = pa; ib = pb - 1;
