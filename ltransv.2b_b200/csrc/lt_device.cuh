@@ -170,6 +170,32 @@ LT_DEVN bool gridcell(const double* __restrict__ q, double X, double Y)
     return (total & 1) != 0;
 }
 
+// Quick decision for a CONVEX element (LtGridTab::convex, checked on the host): the four edge
+// cross products all carry the sign of the element's orientation <=> the point is inside; one
+// of them clearly carries the opposite sign <=> it is outside.  "Clearly" = by more than 1e-9 of
+// the element's area scale, about 1e7 times the rounding error of the products, so the verdict
+// equals gridcell's crossing count; points within that sliver of an edge or a vertex (where the
+// reference's on-edge / on-vertex rules decide) return -1 and take the literal routine.
+LT_DEV int gridcell_quick(const double* __restrict__ q, double X, double Y)
+{
+    const double x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3], y0 = q[4], y1 = q[5], y2 = q[6], y3 = q[7];
+    const double A = (x2 - x0) * (y3 - y1) - (x3 - x1) * (y2 - y0);          // twice the signed area
+    const double sg = A < 0.0 ? -1.0 : 1.0;
+    const double c0 = sg * ((x1 - x0) * (Y - y0) - (y1 - y0) * (X - x0)), c1 = sg * ((x2 - x1) * (Y - y1) - (y2 - y1) * (X - x1));
+    const double c2 = sg * ((x3 - x2) * (Y - y2) - (y3 - y2) * (X - x2)), c3 = sg * ((x0 - x3) * (Y - y3) - (y0 - y3) * (X - x3));
+    const double tol = 1e-9 * fabs(A);
+    const double lo = fmin(fmin(c0, c1), fmin(c2, c3));
+    if (lo > tol) return 1;
+    if (lo < -tol) return 0;
+    return -1;
+}
+LT_DEV bool gridcell_any(const LtGridTab& G, int e0, double X, double Y)
+{   // e0 = 0-based element
+    const double* q = G.ele + (size_t)e0 * 8;
+    const int r = G.convex ? gridcell_quick(q, X, Y) : -1;
+    return r < 0 ? gridcell(q, X, Y) : r != 0;
+}
+
 // setEle (hydro:1414-1532), neighbour-search form.  Returns false for "jumped over
 // an element" (a 0 entry reached, ledger 17).  If all 10 entries are non-zero and none
 // matches, the reference raises nothing and keeps the old element (hydro:1464-1476).
@@ -184,7 +210,7 @@ LT_FE_ATTR bool find_element(const LtGridTab& G, double X, double Y, int& ele)
         int check = __ldg(row + i);
         LT_ASSERT(check >= 0 && check <= G.nE);
         if (check == 0) return false;
-        if (gridcell(G.ele + (size_t)(check - 1) * 8, X, Y)) { ele = check; return true; }
+        if (gridcell_any(G, check - 1, X, Y)) { ele = check; return true; }
     }
     return true;
 }

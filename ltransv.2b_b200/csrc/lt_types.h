@@ -20,6 +20,7 @@ struct LtGridTab {              // one of the rho / u / v grids
     const int*    adj;          // [nE][10] 1-based neighbour element ids, 0 = none
     const uint8_t* mask;        // [nodes]  only read when FreeSlip
     int nE, nodes;
+    int convex;                 // every element is a convex, non-degenerate quad (checked by set_grid)
     // bucket index over element bounding boxes for the whole-grid search (built by set_grid)
     double lx0, ly0, lrcs; int lnx, lny; const int *lptr, *lidx;
 };

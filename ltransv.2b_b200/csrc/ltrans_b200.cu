@@ -184,7 +184,7 @@ __global__ void k_locate(const LtDev D, LtGridTab G, int* __restrict__ ele)
         int c = cy * G.lnx + cx;
         for (int q = __ldg(G.lptr + c); q < __ldg(G.lptr + c + 1); ++q) {
             int e = __ldg(G.lidx + q);
-            if (gridcell(G.ele + (size_t)e * 8, X, Y)) { found = e + 1; break; }
+            if (gridcell_any(G, e, X, Y)) { found = e + 1; break; }
         }
     }
     ele[n] = found;
@@ -618,6 +618,21 @@ static int32_t make_gridtab(ltgpu_ctx* ctx, LtGridTab* G, int nE, int nodes, con
     TRY(upload(ctx, &G->node, nd.data(), nd.size()));
     TRY(upload(ctx, &G->adj, adj.data(), adj.size()));
     G->mask = dmask; G->nE = nE; G->nodes = nodes;
+    {   // gridcell_quick is only valid for convex, non-degenerate quads: all four corner turns must
+        // have the sign of the area, each by a clear margin
+        int convex = 1;
+        for (int e = 0; e < nE && convex; ++e) {
+            const double* q = &ele[(size_t)e * 8];
+            double A = (q[2] - q[0]) * (q[7] - q[5]) - (q[3] - q[1]) * (q[6] - q[4]);
+            if (!(fabs(A) > 0.0)) { convex = 0; break; }
+            for (int i = 0; i < 4; ++i) {
+                int a = i, b = (i + 1) & 3, c = (i + 2) & 3;
+                double turn = (q[b] - q[a]) * (q[4 + c] - q[4 + b]) - (q[4 + b] - q[4 + a]) * (q[c] - q[b]);
+                if (!(turn * (A < 0 ? -1.0 : 1.0) > 1e-6 * fabs(A))) { convex = 0; break; }
+            }
+        }
+        G->convex = convex;
+    }
     {   // bucket index for k_locate: about one element per bucket
         double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
         for (int e = 0; e < nE; ++e)
