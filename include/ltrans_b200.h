@@ -215,7 +215,10 @@ int32_t ltgpu_run_external(ltgpu_ctx* ctx, int32_t p);
 int32_t ltgpu_sync(ltgpu_ctx* ctx, int32_t* bad_particle);
 
 /* Gather particle state (printOutput LTRANS.f90:1617, fin_LTRANS :632-658).
- * Any pointer may be NULL.  status = getStatus (behavior_module.f90:554-574). */
+ * Any pointer may be NULL.  status = getStatus (behavior_module.f90:554-574).
+ * Destinations in page-locked host memory (cudaHostAlloc / cudaHostRegister by the caller)
+ * receive the device copy directly; pageable ones go through the library's pinned bounce
+ * buffers (double buffered: the copy of one column overlaps the memcpy of the previous one). */
 int32_t ltgpu_fetch(ltgpu_ctx* ctx,
     double* x, double* y, double* z, double* age, int32_t* status,
     double* salt, double* temp, int32_t* hitBottom, int32_t* hitLand,

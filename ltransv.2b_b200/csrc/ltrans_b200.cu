@@ -277,6 +277,7 @@ struct ltgpu_ctx {
     unsigned *d_key = nullptr, *d_key2 = nullptr; int *d_idx = nullptr, *d_perm = nullptr, *d_pid = nullptr;
     void* d_cub = nullptr; size_t cub_bytes = 0;
     double* spare8 = nullptr; double* out8 = nullptr;          // bounce buffers of ltgpu_fetch
+    bool direct_pending = false;                               // copies straight into page-locked caller memory in flight
     double* alt8[11] = {}; int* alt4[8] = {}; uint8_t* alt1[2] = {};   // second copy of the per-slot state (re-sort target)
     void* h_out[2] = {nullptr, nullptr};     // pinned bounce buffers for fetch (pageable D2H is 4-5x slower)
     cudaEvent_t out_done[2] = {nullptr, nullptr}; int out_i = 0;
@@ -507,6 +508,16 @@ static int32_t fetch_col(ltgpu_ctx* ctx, V* host, const V* dev)
     V* tmp = (V*)(b ? (void*)ctx->spare8 : (void*)ctx->out8);       // spare8 is free between re-sorts
     k_scatter<V><<<(n + 255) / 256, 256, 0, ctx->compute>>>(dev, tmp, ctx->d_pid, n);
     ctx->launches++;
+    {   // a page-locked destination (cudaHostAlloc / cudaHostRegister by the caller) takes the copy
+        // directly: no bounce buffer, no host memcpy; fetch_flush waits for the stream
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, host) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+            CK(cudaMemcpyAsync(host, tmp, bytes, cudaMemcpyDeviceToHost, ctx->compute));
+            ctx->direct_pending = true;
+            return LTGPU_OK;
+        }
+        cudaGetLastError();
+    }
     CK(cudaMemcpyAsync(ctx->h_out[b], tmp, bytes, cudaMemcpyDeviceToHost, ctx->compute));
     CK(cudaEventRecord(ctx->out_done[b], ctx->compute));
     ctx->pend_host[b] = host; ctx->pend_bytes[b] = bytes;
@@ -521,6 +532,7 @@ static int32_t fetch_col(ltgpu_ctx* ctx, V* host, const V* dev)
 }
 static int32_t fetch_flush(ltgpu_ctx* ctx)
 {
+    if (ctx->direct_pending) { CK(cudaStreamSynchronize(ctx->compute)); ctx->direct_pending = false; }
     for (int b = 0; b < 2; ++b)
         if (ctx->pend_host[b]) {
             CK(cudaEventSynchronize(ctx->out_done[b]));

@@ -232,13 +232,19 @@ class LtransLib:
 
     # -- results ------------------------------------------------------------
     def fetch(self, fields=("x", "y", "z", "age", "status", "salt", "temp", "hitBottom", "hitLand",
-                            "endpoly", "lifespan", "r_ele", "u_ele", "v_ele")):
+                            "endpoly", "lifespan", "r_ele", "u_ele", "v_ele"), out=None):
+        """`out` = {field: preallocated array}: filled in place; page-locked arrays (e.g.
+        torch.empty(..., pin_memory=True).numpy()) receive the device copy directly."""
         n = self.n
         spec = [("x", np.float64), ("y", np.float64), ("z", np.float64), ("age", np.float64),
                 ("status", np.int32), ("salt", np.float64), ("temp", np.float64),
                 ("hitBottom", np.int32), ("hitLand", np.int32), ("endpoly", np.int32),
                 ("lifespan", np.float64), ("r_ele", np.int32), ("u_ele", np.int32), ("v_ele", np.int32)]
-        out = {k: (np.empty(n, dtype=t) if k in fields else None) for k, t in spec}
+        given = out or {}
+        for k, t in spec:
+            if k in given and (given[k].dtype != t or given[k].shape != (n,) or not given[k].flags.c_contiguous):
+                raise ValueError("fetch: out[%r] must be a contiguous %s array of %d" % (k, np.dtype(t).name, n))
+        out = {k: (given[k] if k in given else np.empty(n, dtype=t)) if k in fields else None for k, t in spec}
         rc = self._fn("fetch")(self.ctx, *[_p(out[k]) for k, _ in spec])
         self._check(rc, "fetch")
         return {k: v for k, v in out.items() if v is not None}
