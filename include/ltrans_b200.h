@@ -33,6 +33,9 @@ extern "C" {
 #define LTGPU_E_NODEVICE    3   /* no usable CUDA device -- no CPU fallback    */
 #define LTGPU_E_PARTICLE    4   /* ErrorFlag==0 semantics: a particle hit a    */
                                 /* STOP condition of LTRANS.f90:835-856 etc.   */
+#define LTGPU_W_EVENTS_LOST 5   /* warning of ltgpu_drain_events: the device   */
+                                /* event log overflowed, some ErrorLog lines   */
+                                /* are missing (the drained ones are valid)    */
 
 /* ---- per-particle event codes (ErrorLog.txt formats, LTRANS.f90:761-775) */
 #define LTGPU_EV_INIT_OUT_MAIN   11  /* initially outside main bounds  (LTRANS.f90:377) */
@@ -249,12 +252,29 @@ int32_t ltgpu_reset_hits(ltgpu_ctx* ctx);
  * multi-GPU callers all-reduce these 8 int64 (NCCL sum). */
 int32_t ltgpu_stats(ltgpu_ctx* ctx, int64_t counts[8]);
 
-/* Drain buffered per-particle events in ascending particle id. */
+/* Drain buffered per-particle events (by time step, then ascending particle id = the order
+ * the serial loop writes ErrorLog.txt, LTRANS.f90:761-775).  Call until *n < cap.
+ * The device log holds max(2^20, numpar) events and is emptied into host memory at every
+ * ltgpu_sync / ltgpu_drain_events, so it cannot overflow when the host synchronises at least
+ * once per internal step; with fewer synchronisations (ltgpu_run_external) an overflow drops
+ * the newest events, which is reported ONCE by the return value LTGPU_W_EVENTS_LOST (buf and
+ * *n are still valid) and counted by ltgpu_events_lost. */
 int32_t ltgpu_drain_events(ltgpu_ctx* ctx, ltgpu_event* buf, int32_t cap, int32_t* n);
+int32_t ltgpu_events_lost(ltgpu_ctx* ctx, int64_t* lost);
 
 /* Device pointers of the particle state for device-side gathers (NCCL output
  * gather without a host bounce).  which: 0=x 1=y 2=z 3=age 4=status. */
 int32_t ltgpu_device_ptr(ltgpu_ctx* ctx, int32_t which, void** dptr);
+
+/* Output gather without a host bounce (ncclAllGather of the print-interval
+ * columns): writes column `which` (0=x 1=y 2=z 3=age as double, 4=status as int32,
+ * getStatus behavior_module.f90:554-574) in PARTICLE order into caller-owned DEVICE memory
+ * (numpar elements), asynchronously on the compute stream (ltgpu_stream). */
+int32_t ltgpu_export_device(ltgpu_ctx* ctx, int32_t which, void* dst_device);
+
+/* Measured FP64 FMA rate of the device in TFLOP/s (8 independent chains per thread, best of
+ * 4 launches): the compute roof this FP64 path is reported against next to the HBM one. */
+int32_t ltgpu_fp64_peak(ltgpu_ctx* ctx, double* tflops);
 
 /* Timing helpers used by bench.py: CUDA events recorded on the compute stream
  * (torch.cuda.Event only sees torch's current stream). */

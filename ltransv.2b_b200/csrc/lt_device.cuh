@@ -204,7 +204,9 @@ LT_DEV bool gridcell_any(const LtGridTab& G, int e0, double X, double Y)
 #endif
 LT_FE_ATTR bool find_element(const LtGridTab& G, double X, double Y, int& ele)
 {
-    LT_ASSERT(ele >= 1 && ele <= G.nE);
+    // ele == 0: never located (start-up screen, ltgpu_screen_initial).  The reference would index
+    // its adjacency table out of bounds here; reported as "not in element" instead of faulting.
+    if (ele < 1 || ele > G.nE) return false;
     const int* row = G.adj + (size_t)(ele - 1) * 10;
     for (int i = 0; i < 10; ++i) {
         int check = __ldg(row + i);

@@ -241,6 +241,22 @@ __global__ void k_lonlat(const LtDev D, int spherical, double lonmin, double lat
     }
 }
 
+// FP64 FMA throughput of the device: the second roof of this path.  8 independent
+// FMA chains per thread, 1024 resident threads per SM.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* __restrict__ out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 __global__ void k_fill_i32(int* p, int v, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,7 +281,8 @@ struct ltgpu_ctx {
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
     // events
     std::vector<ltgpu_event> host_events;
-    int* d_bad = nullptr; int* d_nev = nullptr; int evcap = 1 << 20; int ev_read = 0;
+    int* d_bad = nullptr; int* d_nev = nullptr; int evcap = 1 << 20;
+    long long ev_lost = 0, ev_lost_reported = 0;   // events dropped because the device log was full
     unsigned long long* d_stats = nullptr; int* d_status = nullptr;
     double last_ix3 = -1e300;
     long long launches = 0;
@@ -542,6 +559,27 @@ static int32_t fetch_flush(ltgpu_ctx* ctx)
     return LTGPU_OK;
 }
 
+// Move the device event log to the host and recycle it.  Called at the library's synchronisation
+// points (ltgpu_sync, ltgpu_drain_events) with the compute stream idle, so the log only has to
+// hold the events of the steps queued between two of them; what did not fit is counted in
+// ev_lost and reported by ltgpu_drain_events / ltgpu_events_lost.
+static int32_t pull_events(ltgpu_ctx* ctx)
+{
+    if (!ctx->d_nev) return LTGPU_OK;
+    int nev = 0;
+    CK(cudaMemcpyAsync(&nev, ctx->d_nev, 4, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    if (nev <= 0) return LTGPU_OK;
+    const int keep = std::min(nev, ctx->evcap);
+    if (nev > ctx->evcap) ctx->ev_lost += (long long)nev - ctx->evcap;
+    const size_t old = ctx->host_events.size();
+    ctx->host_events.resize(old + keep);
+    CK(cudaMemcpyAsync(ctx->host_events.data() + old, ctx->D.ev, sizeof(ltgpu_event) * keep, cudaMemcpyDeviceToHost, ctx->compute));
+    CK(cudaMemsetAsync(ctx->d_nev, 0, 4, ctx->compute));
+    CK(cudaStreamSynchronize(ctx->compute));
+    return LTGPU_OK;
+}
+
 extern "C" {
 
 int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
@@ -581,6 +619,7 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     ctx->sort_on = !(so && so[0] == '0');
     { const char* se = getenv("LTGPU_SORT_EVERY"); if (se && atoi(se) > 0) ctx->sort_every = atoi(se); }
     { const char* sm = getenv("LTGPU_SORT_MODE"); ctx->sort_mode = sm ? std::max(0, std::min(127, atoi(sm))) : 32; }
+    { const char* ec = getenv("LTGPU_EVCAP"); ctx->evcap = ec && atoi(ec) > 0 ? atoi(ec) : 0; }   // 0: sized by set_particles
     *out = ctx;
     return LTGPU_OK;
 }
@@ -732,7 +771,12 @@ int32_t ltgpu_set_grid(ltgpu_ctx* ctx, int32_t vi, int32_t uj, int32_t ui, int32
         *q.p = p;
     }
     // staging: one record = zeta + u + v + w + aks + salt + temp, at the host dtype (<= 8 B)
-    ctx->stage_bytes = (rn + un * us + vn * us + 2 * rn * ws + 2 * rn * us) * 8;
+    // (push_hydro pads every field to 16 bytes)
+    {
+        const size_t cnt[7] = {rn, un * us, vn * us, rn * ws, rn * ws, rn * us, rn * us};
+        ctx->stage_bytes = 0;
+        for (size_t c : cnt) ctx->stage_bytes += (c * 8 + 15) & ~(size_t)15;
+    }
     for (int i = 0; i < 2; ++i) {
         CK(cudaMallocHost(&ctx->h_stage[i], ctx->stage_bytes));
         void* d = nullptr; CK(cudaMalloc(&d, ctx->stage_bytes)); ctx->owned.push_back(d); ctx->d_stage[i] = d;
@@ -831,6 +875,9 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
         k_locate<<<blocks, 128, 0, ctx->compute>>>(D, D.V, D.v_ele);
         ctx->launches += 3;
     }
+    // a particle raises at most one event per internal step, so max(2^20, n) entries cannot
+    // overflow between two synchronisation points that are at most one step apart
+    if (ctx->evcap <= 0) ctx->evcap = std::max(1 << 20, n);
     TRY(dalloc(ctx, &D.ev, (size_t)ctx->evcap)); D.evcap = ctx->evcap;
     TRY(dalloc(ctx, &ctx->d_nev, 1)); TRY(dalloc(ctx, &ctx->d_bad, 1));
     D.nev = ctx->d_nev; D.bad = ctx->d_bad;
@@ -911,6 +958,7 @@ int32_t ltgpu_push_hydro(ltgpu_ctx* ctx, int32_t dtype, const void* zeta, const 
     for (int i = 0; i < 7; ++i) {
         off[i] = o;
         if (i >= 5 && !have_st) continue;
+        ARG(o + cnt[i] * e <= ctx->stage_bytes, "push_hydro: record larger than the staging buffer");
         memcpy(hs + o, src[i], cnt[i] * e);                    // pageable -> pinned
         o += (cnt[i] * e + 15) & ~(size_t)15;
     }
@@ -1014,7 +1062,7 @@ int32_t ltgpu_sync(ltgpu_ctx* ctx, int32_t* bad_particle)
     if (ctx->d_bad) CK(cudaMemcpy(&bad, ctx->d_bad, 4, cudaMemcpyDeviceToHost));
     if (bad_particle) *bad_particle = bad == INT_MAX ? 0 : bad;
     if (bad != INT_MAX) { ctx->err = "a particle hit a STOP condition (ErrorFlag outside 1..3)"; return LTGPU_E_PARTICLE; }
-    return LTGPU_OK;
+    return pull_events(ctx);
 }
 
 int32_t ltgpu_fetch(ltgpu_ctx* ctx, double* x, double* y, double* z, double* age, int32_t* status,
@@ -1083,7 +1131,7 @@ int32_t ltgpu_stats(ltgpu_ctx* ctx, int64_t counts[8])
     CK(cudaMemcpyAsync(&nev, ctx->d_nev, 4, cudaMemcpyDeviceToHost, ctx->compute));
     CK(cudaStreamSynchronize(ctx->compute));
     for (int k = 0; k < 8; ++k) counts[k] = (int64_t)h[k];
-    counts[5] = (int64_t)(nev - ctx->ev_read) + (int64_t)ctx->host_events.size();
+    counts[5] = (int64_t)std::min(nev, ctx->evcap) + (int64_t)ctx->host_events.size();
     return LTGPU_OK;
 }
 
@@ -1092,17 +1140,7 @@ int32_t ltgpu_drain_events(ltgpu_ctx* ctx, ltgpu_event* buf, int32_t cap, int32_
     if (!ctx || !buf || !n || cap < 0) return LTGPU_E_ARG;
     ARG(ctx->have_particles, "drain_events before set_particles");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->compute));
-    int nev = 0;
-    CK(cudaMemcpy(&nev, ctx->d_nev, 4, cudaMemcpyDeviceToHost));
-    nev = std::min(nev, ctx->evcap);
-    if (nev > ctx->ev_read) {
-        size_t old = ctx->host_events.size();
-        ctx->host_events.resize(old + (nev - ctx->ev_read));
-        CK(cudaMemcpy(ctx->host_events.data() + old, ctx->D.ev + ctx->ev_read, sizeof(ltgpu_event) * (nev - ctx->ev_read),
-                      cudaMemcpyDeviceToHost));
-        ctx->ev_read = nev;
-    }
+    TRY(pull_events(ctx));
     // ErrorLog.txt order of the serial loop: by time step, then ascending particle id
     std::sort(ctx->host_events.begin(), ctx->host_events.end(), [](const ltgpu_event& a, const ltgpu_event& b) {
         return a.time != b.time ? a.time < b.time : a.particle < b.particle; });
@@ -1110,6 +1148,19 @@ int32_t ltgpu_drain_events(ltgpu_ctx* ctx, ltgpu_event* buf, int32_t cap, int32_
     memcpy(buf, ctx->host_events.data(), sizeof(ltgpu_event) * k);
     ctx->host_events.erase(ctx->host_events.begin(), ctx->host_events.begin() + k);
     *n = k;
+    if (ctx->ev_lost > ctx->ev_lost_reported) {
+        ctx->err = std::to_string(ctx->ev_lost - ctx->ev_lost_reported) + " per-particle events were dropped: the device log (" +
+                   std::to_string(ctx->evcap) + " entries) filled up between two synchronisation points";
+        ctx->ev_lost_reported = ctx->ev_lost;
+        return LTGPU_W_EVENTS_LOST;
+    }
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_events_lost(ltgpu_ctx* ctx, int64_t* lost)
+{
+    if (!ctx || !lost) return LTGPU_E_ARG;
+    *lost = (int64_t)ctx->ev_lost;
     return LTGPU_OK;
 }
 
@@ -1117,6 +1168,7 @@ int32_t ltgpu_device_ptr(ltgpu_ctx* ctx, int32_t which, void** dptr)
 {
     if (!ctx || !dptr) return LTGPU_E_ARG;
     ARG(ctx->have_particles, "device_ptr before set_particles");
+    CK(cudaSetDevice(ctx->device));
     LtDev& D = ctx->D;
     // slots are re-sorted by cell; hand out a particle-order copy (valid until the next call)
     int n = D.n;
@@ -1129,6 +1181,49 @@ int32_t ltgpu_device_ptr(ltgpu_ctx* ctx, int32_t which, void** dptr)
         k_scatter<int><<<(n + 255) / 256, 256, 0, ctx->compute>>>(ctx->d_status, (int*)ctx->out8, ctx->d_pid, n);
         ctx->launches += 2; *dptr = ctx->out8;
     } else { ctx->err = "device_ptr: which out of range"; return LTGPU_E_ARG; }
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_export_device(ltgpu_ctx* ctx, int32_t which, void* dst_device)
+{
+    if (!ctx || !dst_device) return LTGPU_E_ARG;
+    ARG(ctx->have_particles, "export_device before set_particles");
+    CK(cudaSetDevice(ctx->device));
+    LtDev& D = ctx->D; const int n = D.n, blocks = (n + 255) / 256;
+    if (which >= 0 && which <= 3) {
+        const double* src = which == 0 ? D.x : which == 1 ? D.y : which == 2 ? D.z : D.age;
+        k_scatter<double><<<blocks, 256, 0, ctx->compute>>>(src, (double*)dst_device, ctx->d_pid, n);
+        ctx->launches++;
+    } else if (which == 4) {
+        k_status<<<blocks, 256, 0, ctx->compute>>>(D, ctx->d_status);
+        k_scatter<int><<<blocks, 256, 0, ctx->compute>>>(ctx->d_status, (int*)dst_device, ctx->d_pid, n);
+        ctx->launches += 2;
+    } else { ctx->err = "export_device: which out of range"; return LTGPU_E_ARG; }
+    CK(cudaGetLastError());
+    return LTGPU_OK;
+}
+
+int32_t ltgpu_fp64_peak(ltgpu_ctx* ctx, double* tflops)
+{
+    if (!ctx || !tflops) return LTGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, ctx->device));
+    const int blocks = pr.multiProcessorCount * 4, iters = 4096;
+    double* d = nullptr; CK(cudaMalloc(&d, sizeof(double) * blocks * 256));
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(a, ctx->compute));
+        k_fp64_peak<<<blocks, 256, 0, ctx->compute>>>(d, iters, 0.999999, 1e-6);
+        CK(cudaEventRecord(b, ctx->compute));
+        CK(cudaEventSynchronize(b));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, a, b));
+        ctx->launches++;
+        const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    *tflops = best;
     return LTGPU_OK;
 }
 

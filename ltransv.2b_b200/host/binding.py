@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-LTGPU_OK, LTGPU_E_ARG, LTGPU_E_CUDA, LTGPU_E_NODEVICE, LTGPU_E_PARTICLE = 0, 1, 2, 3, 4
+LTGPU_OK, LTGPU_E_ARG, LTGPU_E_CUDA, LTGPU_E_NODEVICE, LTGPU_E_PARTICLE, LTGPU_W_EVENTS_LOST = 0, 1, 2, 3, 4, 5
 LTGPU_F32, LTGPU_F64 = 4, 8
 LTGPU_RNG_PHILOX = 1
 
@@ -93,6 +93,7 @@ class LtransLib:
         self.prefix = prefix
         self.ctx = C.c_void_p()
         self.n = 0
+        self.events_lost = 0
         self._keep = []       # host buffers that must outlive an async push
         last = getattr(self.lib, prefix + "last_error", None)
         if last is not None:
@@ -271,11 +272,30 @@ class LtransLib:
         self._check(self._fn("stats")(self.ctx, c), "stats")
         return np.array(list(c), dtype=np.int64)
 
-    def drain_events(self, cap=4096):
-        buf = (Event * cap)()
-        n = C.c_int32(0)
-        self._check(self._fn("drain_events")(self.ctx, buf, C.c_int32(cap), C.byref(n)), "drain_events")
-        return [(buf[i].particle, buf[i].code, buf[i].time) for i in range(n.value)]
+    def drain_events(self, cap=4096, everything=False):
+        """One ltgpu_drain_events call (at most `cap` events), or with everything=True repeated
+        calls until the log is empty.  An overflow of the device log (LTGPU_W_EVENTS_LOST) is
+        not an error here: the count is kept in `self.events_lost`."""
+        out = []
+        while True:
+            buf = (Event * cap)()
+            n = C.c_int32(0)
+            rc = self._fn("drain_events")(self.ctx, buf, C.c_int32(cap), C.byref(n))
+            if rc == LTGPU_W_EVENTS_LOST:
+                self.events_lost = self.lost_events()
+            else:
+                self._check(rc, "drain_events")
+            out += [(buf[i].particle, buf[i].code, buf[i].time) for i in range(n.value)]
+            if not everything or n.value < cap:
+                return out
+
+    def lost_events(self):
+        f = getattr(self.lib, self.prefix + "events_lost", None)
+        if f is None:
+            return 0
+        lost = C.c_int64(0)
+        self._check(f(self.ctx, C.byref(lost)), "events_lost")
+        return int(lost.value)
 
     # -- device-only helpers (bench / NCCL gather) ---------------------------
     def timer_start(self):
@@ -299,3 +319,15 @@ class LtransLib:
         p = C.c_void_p()
         self._check(self._fn("device_ptr")(self.ctx, C.c_int32(which), C.byref(p)), "device_ptr")
         return p.value
+
+    def export_device(self, which, dst_ptr):
+        """column `which` (0=x 1=y 2=z 3=age f64, 4=status i32) in particle order into device memory"""
+        self._check(self._fn("export_device")(self.ctx, C.c_int32(which), C.c_void_p(dst_ptr)), "export_device")
+
+    def fp64_peak(self):
+        t = C.c_double(0)
+        self._check(self._fn("fp64_peak")(self.ctx, C.byref(t)), "fp64_peak")
+        return t.value
+
+    def stream(self):
+        return int(self._fn("stream")(self.ctx) or 0)

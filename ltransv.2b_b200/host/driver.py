@@ -81,7 +81,7 @@ class Run:
         return self.finish()
 
     def _errors(self):
-        ev = self.e.drain_events(1 << 16)
+        ev = self.e.drain_events(1 << 16, everything=True)
         if ev:
             formats.append_errorlog(os.path.join(self.outdir, "ErrorLog.txt"), ev)
 

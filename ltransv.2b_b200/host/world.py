@@ -362,9 +362,10 @@ class World:
         ok[:, -margin - 1:] = False
         return ok
 
-    def seed_particles(self, n, seed=1234, margin=2, dob_max=0.0):
+    def seed_particles(self, n, seed=1234, margin=2, dob_max=0.0, locate=True):
         """Random release points (x, y, z, dob) inside water, >= margin cells off land,
-        plus their rho/u/v elements (what setEle_all hydro:1536 would find)."""
+        plus their rho/u/v elements (what setEle_all hydro:1536 would find); locate=False
+        returns None for the elements (ltgpu_set_particles then locates on the device)."""
         rng = np.random.Generator(np.random.Philox(seed))
         cells = np.argwhere(self._interior_water(margin)[:-1, :-1])
         c = cells[rng.integers(0, len(cells), size=n)]
@@ -374,7 +375,7 @@ class World:
         hloc = self.h[j0, i0]
         z = -hloc * (0.08 + 0.84 * rng.random(n))
         dob = np.zeros(n) if dob_max <= 0 else np.floor(rng.random(n) * dob_max / 120.0) * 120.0
-        r, u, v = self.locate(x, y, fi, fj)
+        r, u, v = self.locate(x, y, fi, fj) if locate else (None, None, None)
         return x, y, z, dob, r, u, v
 
     def locate(self, x, y, fi, fj):

@@ -375,3 +375,73 @@ def test_abi_misc_calls():
     g.reset_hits()
     assert g.fetch(("hitLand",))["hitLand"].sum() == 0
     g.destroy()
+
+
+def test_odd_grid_f64_push_with_salt_temp():
+    """every field of a pushed record is padded to 16 bytes in the staging buffers; an
+    odd x odd grid with float64 records and salt / temp is the case whose padding used to run past
+    the allocation."""
+    odd = dict(ni=41, nj=37, us=10)
+    rg, ro, res, ev, st, fg, fo = _pair(300, 3, world_kw=odd, dtype=np.float64, field_dtype=8, **dict(PASSIVE, SaltTempOn=1))
+    assert rg == ro
+    assert_parity(res, 1e-9)
+    assert np.allclose(fg["salt"], fo["salt"], rtol=1e-12, atol=0)
+
+
+def test_event_log_recycles_and_reports_overflow(monkeypatch):
+    """The device event log is emptied at every synchronisation point, so a host that synchronises
+    once per internal step loses nothing however long the run; when it is too small for the steps
+    queued between two synchronisations the loss is counted and reported, not silent."""
+    from oracle.oracle import Oracle
+    from ltrans_b200.host.binding import LTGPU_W_EVENTS_LOST
+    kw = dict(PASSIVE, HTurbOn=1, ConstantHTurb=2000.0, ErrorFlag=1)          # huge kicks: many particles raise events
+    w = World(**SMALL); n = 300
+    prm = make_params(w, n, **kw)
+    monkeypatch.setenv("LTGPU_EVCAP", str(n))                                 # one step's worth
+    g, o = LtransLib(), Oracle()
+    setup(g, w, prm, n); setup(o, w, prm, n)
+    for it in range(1, 31):
+        g.step(1, it); o.step(1, it)
+        assert g.sync() == o.sync()
+    eg, eo = g.drain_events(64, everything=True), o.drain_events(1 << 16)
+    assert len(eo) > n and eg == eo and g.lost_events() == 0                  # more events than the log holds, none lost
+    assert g.stats()[5] == 0
+    g.destroy(); o.destroy()
+    monkeypatch.setenv("LTGPU_EVCAP", "8")
+    g = LtransLib()
+    setup(g, w, prm, n)
+    g.run_external(1)                                                         # 30 steps queued without a synchronisation
+    g.sync()
+    got = g.drain_events(1 << 16)
+    assert g.events_lost > 0 and len(got) + g.events_lost == len(eo)
+    assert set(got) <= set(eo)
+    import ctypes as C
+    from ltrans_b200.host.binding import Event
+    buf = (Event * 4)(); k = C.c_int32(0)
+    assert g.lib.ltgpu_drain_events(g.ctx, buf, C.c_int32(4), C.byref(k)) == 0   # the warning is raised once
+    g.destroy()
+
+
+def test_unlocated_particle_does_not_fault():
+    """a particle released outside every element keeps element id 0; with ErrorFlag = 2
+    and mortality off it is still stepped.  It must raise 'not in rho element', not index the
+    adjacency table out of bounds."""
+    w = World(**SMALL); n = 64
+    prm = make_params(w, n, **dict(PASSIVE, ErrorFlag=2))
+    g = LtransLib().create(prm)
+    g.set_grid(w.grid()); g.set_bounds(w.bounds())
+    x, y, z, dob, r, u, v = w.seed_particles(n)
+    x[:4] = w.x_r.min() - 5e4                                                 # far outside the grid
+    g.set_particles(x, y, z, dob, None, None, None, None)
+    rc, counts, bad = g.screen_initial()
+    assert rc == 0 and counts[0] == 4
+    for k in range(3):
+        g.push_hydro(w.record(k))
+    g.run_external(1)
+    assert g.sync() == (0, 0)
+    ev = g.drain_events(1 << 12)
+    codes = {c for (p_, c, t) in ev if p_ <= 4}
+    assert 21 in codes and 11 in codes
+    f = g.fetch(("x", "status"))
+    assert np.all(f["status"][:4] == -1) and np.isfinite(f["x"]).all()
+    g.destroy()
