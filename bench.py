@@ -55,7 +55,7 @@ CONFIGS = {
     3: dict(name="config3 (BASELINE configs[2])", b_alg=4072, particles=10_000_000,
             world=dict(ni=120, nj=80, us=20, dlon=0.02, dlat=0.018), grid="120x80 rho, us 20, ws 21",
             prm=dict(Behavior=4, settlementon=1, holesExist=1, mortality=1, TrackCollisions=0, ErrorFlag=3,
-                     pediage=3600.0, deadage=3 * 3600.0, HTurbOn=1, VTurbOn=1, vturb_full_sigs=1),
+                     pediage=3600.0, deadage=40 * 3600.0, HTurbOn=1, VTurbOn=1, vturb_full_sigs=1),
             desc="Chesapeake-scale synthetic ROMS, oyster larvae (Behavior 4), HTurb+VTurb, 64 settlement "
                  "polygons with holes, mortality", cpu_particles=100_000, npoly=64),
 }

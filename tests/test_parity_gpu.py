@@ -441,7 +441,7 @@ def test_unlocated_particle_does_not_fault():
     assert g.sync() == (0, 0)
     ev = g.drain_events(1 << 12)
     codes = {c for (p_, c, t) in ev if p_ <= 4}
-    assert 21 in codes and 11 in codes
+    assert codes == {11, 23}          # start-up screen, then setEle's error (the v-grid test is the last to set it, hydro:1497)
     f = g.fetch(("x", "status"))
     assert np.all(f["status"][:4] == -1) and np.isfinite(f["x"]).all()
     g.destroy()
