@@ -45,17 +45,17 @@ CONFIGS = {
             world=dict(ni=1024, nj=768, us=36, hmin=50.0, hmax=3000.0, dlon=0.02, dlat=0.018, speed=0.9),
             grid="1024x768 rho, us 36, ws 37",
             prm=dict(Behavior=6, sink=0.002, settlementon=0, mortality=0, TrackCollisions=0, ErrorFlag=3,
-                     OpenOceanBoundary=1, HTurbOn=1, VTurbOn=1, vturb_full_sigs=1),
+                     OpenOceanBoundary=1, HTurbOn=1, VTurbOn=1),
             desc="Gulf-scale synthetic ROMS, buoyant particles (Behavior 6), HTurb+VTurb, open boundary",
             cpu_particles=100_000),
     2: dict(name="config2 (BASELINE configs[1])", b_alg=3624, particles=1_000_000,
             world=dict(), grid="130x130 rho, us 20, ws 21",
-            prm=dict(Behavior=0, settlementon=0, mortality=0, TrackCollisions=0, ErrorFlag=1, HTurbOn=1, VTurbOn=1, vturb_full_sigs=1),
+            prm=dict(Behavior=0, settlementon=0, mortality=0, TrackCollisions=0, ErrorFlag=1, HTurbOn=1, VTurbOn=1),
             desc="Baymouth-shape synthetic ROMS, passive particles, HTurb+VTurb", cpu_particles=100_000),
     3: dict(name="config3 (BASELINE configs[2])", b_alg=4072, particles=10_000_000,
             world=dict(ni=120, nj=80, us=20, dlon=0.02, dlat=0.018), grid="120x80 rho, us 20, ws 21",
             prm=dict(Behavior=4, settlementon=1, holesExist=1, mortality=1, TrackCollisions=0, ErrorFlag=3,
-                     pediage=3600.0, deadage=40 * 3600.0, HTurbOn=1, VTurbOn=1, vturb_full_sigs=1),
+                     pediage=3600.0, deadage=40 * 3600.0, HTurbOn=1, VTurbOn=1),
             desc="Chesapeake-scale synthetic ROMS, oyster larvae (Behavior 4), HTurb+VTurb, 64 settlement "
                  "polygons with holes, mortality", cpu_particles=100_000, npoly=64),
 }
@@ -65,7 +65,7 @@ NREC = 5            # distinct hydro records kept on the host, visited 0,1,2,3,4
 def config_dict(cfg, n, world_size, prm):
     return {"workload": f"{cfg['name']}: {cfg['desc']}; {n} particles/GPU; {prm.dt // prm.idt} internal steps per step",
             "particles_per_gpu": n, "grid": cfg["grid"], "internal_steps_per_step": prm.dt // prm.idt,
-            "vturb_full_sigs": int(prm.vturb_full_sigs), "field_storage": "f32 (lossless), [node][level][4-slot ring]",
+            "vturb_full_sigs": int(not prm.vturb_window_sigs), "field_storage": "f32 (lossless), [node][level][4-slot ring]",
             "rng": "philox4x32-10 keyed (seed; particle id, step, block)", "parallelism": f"particle slices x{world_size}, fields replicated",
             "l2": "particle state + fields exceed L2 at 12.5 M particles; a 256 MiB buffer is also written between timed steps"}
 

@@ -105,9 +105,11 @@ typedef struct ltgpu_params {
     int32_t FreeSlip;
     int32_t rng_mode;          /* LTGPU_RNG_PHILOX (device has no MT19937)      */
     int32_t field_dtype;       /* LTGPU_F32 or LTGPU_F64 device field storage   */
-    int32_t vturb_full_sigs;   /* 0 (default): VTurb examines SIGS on the 32-knot window it builds;
-                                * 1: also sweeps every interval of the 4*ws-knot fit for SigErr, as
-                                * the reference does (ver_turb:278-279), ~+35 % of the VTurb kernel */
+    int32_t vturb_window_sigs; /* 0 (default): reference semantics -- SIGS examines every interval of the
+                                * 4*ws-knot VTurb fit and any SigErr sends the whole particle-step to
+                                * linint (ver_turb:278-279, 300-336).  1 (opt-in approximation): only the
+                                * 32 knots around the particle are examined, so the fall-back fires
+                                * ~30 % less often than the reference's */
     int32_t reserved1;
 } ltgpu_params;
 

@@ -486,42 +486,17 @@ LT_DEV bool newton_step(NewtonState& q, double& out, int& err)
     return false;
 }
 
-// SIGS classification of one interval (tension:314-527, 638-760).  Returns true when the
-// tension factor is known (`sigma`); false when the convexity Newton solve is needed
-// (TP1, SIG0 filled).  The monotonicity secant iteration (rare: data with an inflection
-// inside the interval) is solved here.
-LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2, double& sigma, double& TP1o, double& SIG0, int& err)
+// The secant / bisection solve of SIGS' monotonicity branch (tension:638-760) for one interval with
+// chord slope S, end slopes S1, S2 (D1 = S - S1, D2 = S2 - S, D1 D2 < 0) that has passed the
+// early exits (S1 S >= 0, S2 S >= 0, D0 > 0, S T0 < 0).  Rare: data with an inflection inside the
+// interval.  err = 1 when the loop cannot terminate (see below).
+LT_DEVN double sigs_monotone_solve(double S, double S1, double S2, double D1, double D2, double D0, int& err)
 {
     const double SBIG = 85.0, RTOL = LT_RTOL, FTOL = 0.0;
-    double S = qdiv(Y2 - Y1, DX);
-    double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
-#ifdef LT_DEBUG_TRACE
-    atomicAdd(&g_dbgcnt2[7], 1ull);                                       // intervals classified
-#endif
-    if ((D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0)) { sigma = SBIG; return true; }
-    double SIG = 0.0;
-    if (D1D2 >= 0.0) {
-        if (D1D2 == 0.0) { sigma = 0.0; return true; }
-        double T = fmax(qdiv(D1, D2), qdiv(D2, D1));
-        if (T <= 2.0) { sigma = 0.0; return true; }
-#ifdef LT_DEBUG_TRACE
-        atomicAdd(&g_dbgcnt2[4], 1ull);                                   // convexity solves (T > 2)
-        if (T > 2.0245 && T < 2.047) atomicAdd(&g_dbgcnt2[5], 1ull);      // ... inside the band where the Newton loop can cycle
-        if (T > 2.02 && T < 2.10) atomicAdd(&g_dbgcnt2[6], 1ull);
-#endif
-        TP1o = T + 1.0;
-        SIG0 = sig_guess(T);                               // reference: SQRT(10 T - 20) (tension:524)
-        return false;
-    }
-    // monotonicity :638-760
-    if (S1 * S < 0.0 || S2 * S < 0.0) { sigma = 0.0; return true; }
-    double T0 = 3.0 * S - S1 - S2;
-    double D0 = T0 * T0 - S1 * S2;
-    if (D0 <= 0.0 || S * T0 >= 0.0) { sigma = 0.0; return true; }
     double SGN = copysign(1.0, S);
-    SIG = SBIG;
+    double SIG = SBIG;
     double FMAX = qdiv(SGN * (SIG * S - S1 - S2), SIG - 2.0);
-    if (FMAX <= 0.0) { sigma = SBIG; return true; }
+    if (FMAX <= 0.0) return SBIG;
     double STOL = RTOL * SIG, F = FMAX, F0 = qdiv(SGN * D0, 3.0 * (D1 - D2)), FNEG = F0;
     double DSIG = SIG, DMAX = SIG, D1PD2 = D1 + D2, A = 0.0, E = 0.0;
     bool CONT = true;                                  // ledger 18
@@ -533,7 +508,7 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
     // oracle shares reaches the same verdict ~50 ms later.
     for (;;) {
         DSIG = qdiv(-F * DSIG, F - F0);
-        if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { LT_DBG_COUNT(3); err = 1; sigma = 0.0; return true; } continue; }
+        if (fabs(DSIG) > fabs(DMAX) || DSIG * DMAX > 0.0) { DSIG = DMAX; F0 = FNEG; if (++NIT > 100000) { LT_DBG_COUNT(3); err = 1; return 0.0; } continue; }
         if (fabs(DSIG) < STOL / 2.0) DSIG = -copysign(STOL / 2.0, DMAX);
         SIG = SIG + DSIG;
         F0 = F;
@@ -561,13 +536,13 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
         if (++NIT > 100000) {
             LT_DBG_COUNT(3);
 #ifdef LT_DEBUG_TRACE
-            g_dbgcase[0] = DX; g_dbgcase[1] = Y1; g_dbgcase[2] = Y2; g_dbgcase[3] = S1; g_dbgcase[4] = S2; g_dbgcase[5] = SIG; g_dbgcase[6] = DSIG; g_dbgcase[7] = F;
+            g_dbgcase[1] = S; g_dbgcase[3] = S1; g_dbgcase[4] = S2; g_dbgcase[5] = SIG; g_dbgcase[6] = DSIG; g_dbgcase[7] = F;
 #endif
-            err = 1; sigma = 0.0; return true;
+            err = 1; return 0.0;
         }
         STOL = RTOL * SIG;
         if (fabs(DMAX) <= STOL || (F >= 0.0 && F <= FTOL) || fabs(F) <= RTOL) break;
-        if (!(F == F)) { LT_DBG_COUNT(6); err = 1; sigma = 0.0; return true; }
+        if (!(F == F)) { LT_DBG_COUNT(6); err = 1; return 0.0; }
         DMAX = DMAX + DSIG;
         if (F0 * F > 0.0 && fabs(F) >= fabs(F0)) { DSIG = DMAX; F0 = FNEG; continue; }
         if (F0 * F <= 0.0) {
@@ -577,8 +552,51 @@ LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2
         }
     }
     LT_DBG_MAX(4, NIT);
-    sigma = fmin(SIG, SBIG);
+    return fmin(SIG, SBIG);
+}
+
+// SIGS classification of one interval (tension:314-527, 638-760) from its chord slope S and end
+// slopes S1, S2.  Returns true when the tension factor is known (`sigma`); false when the
+// convexity Newton solve is needed (T filled: TP1 = T + 1, start value sig_guess(T)).
+LT_DEV bool sigs_classify_s(double S, double S1, double S2, double& sigma, double& T, int& err)
+{
+    const double SBIG = 85.0;
+    const double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
+#ifdef LT_DEBUG_TRACE
+    atomicAdd(&g_dbgcnt2[7], 1ull);                                       // intervals classified
+#endif
+    if ((D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0)) { sigma = SBIG; return true; }
+    sigma = 0.0;
+    if (D1D2 >= 0.0) {
+        if (D1D2 == 0.0) return true;
+        // T = MAX(D1/D2, D2/D1) is the quotient with the larger magnitude on top; it can only
+        // exceed 2 when that magnitude exceeds twice the other, so most intervals skip the division
+        const double a = fabs(D1), b = fabs(D2), hi = fmax(a, b), lo = fmin(a, b);
+        if (!(hi > 2.0 * lo)) return true;
+        T = qdiv(hi, lo);
+        if (T <= 2.0) return true;
+#ifdef LT_DEBUG_TRACE
+        atomicAdd(&g_dbgcnt2[4], 1ull);                                   // convexity solves (T > 2)
+        if (T > 2.0245 && T < 2.047) atomicAdd(&g_dbgcnt2[5], 1ull);      // ... inside the band where the Newton loop can cycle
+        if (T > 2.02 && T < 2.10) atomicAdd(&g_dbgcnt2[6], 1ull);
+#endif
+        return false;
+    }
+    // monotonicity :638-660
+    if (S1 * S < 0.0 || S2 * S < 0.0) return true;
+    const double T0 = 3.0 * S - S1 - S2;
+    const double D0 = T0 * T0 - S1 * S2;
+    if (D0 <= 0.0 || S * T0 >= 0.0) return true;
+    sigma = sigs_monotone_solve(S, S1, S2, D1, D2, D0, err);
     return true;
+}
+LT_DEVN bool sigs_classify(double DX, double Y1, double Y2, double S1, double S2, double& sigma, double& TP1o, double& SIG0, int& err)
+{
+    double T = 0.0;
+    if (sigs_classify_s(qdiv(Y2 - Y1, DX), S1, S2, sigma, T, err)) return true;
+    TP1o = T + 1.0;
+    SIG0 = sig_guess(T);                               // reference: SQRT(10 T - 20) (tension:524)
+    return false;
 }
 
 

@@ -668,7 +668,7 @@ struct VtCtx {
             }
         }
     }
-    // Optional (ltgpu_params.vturb_full_sigs): the reference's SIGS sweeps all p2 - 1 intervals of
+    // Round-1 fused kernel only (unless ltgpu_params.vturb_window_sigs): the reference's SIGS sweeps all p2 - 1 intervals of
     // the fit and any SigErr sends the whole particle-step to linint (ver_turb:278-279, 300-336),
     // the window above only sees its own intervals.  This pass streams over every knot (values,
     // YPC1 slopes, T), keeps nothing, and runs the Newton loop for the intervals whose T lies in
@@ -782,7 +782,7 @@ LT_DEV void vturb_particle(const LtDev& D, int n)
     V.ZN = lag(D.LW4, V.zl[0][V.ws - 1], V.zl[1][V.ws - 1], V.zl[2][V.ws - 1]);
     V.H = (V.ZN - V.Z1) * rp2; V.rH = qrcp(V.H);
     V.ka = 1; V.kb = 0; V.ia = 1; V.ib = 0;
-    if (D.P.vturb_full_sigs) V.sweep();
+    if (!D.P.vturb_window_sigs) V.sweep();
     const Rng g = make_rng(D, n);
     const double deltat = 2.0;
     const int loop = D.P.idt / 2;                                       // :282-283

@@ -59,6 +59,10 @@ struct LtDev {
     double *s_depth, *s_angle, *s_zeb, *s_zec, *s_zef, *s_pzb, *s_pzc, *s_pzf, *s_zpar,
            *s_nx, *s_ny, *s_advz, *s_pu, *s_pv, *s_turbv;
     uint8_t* s_act;
+    // VTurb scratch handed from k_vbuild to k_vwalk for one chunk of particles (lt_vturb.cuh):
+    // vw[row][i]: rows 0..VW-1 knot values, VW..2VW-1 knot slopes, 2VW..3VW-1 tension factors of the
+    // window of chunk-local particle i; vz1 / vzn the knot line; vka = first knot | SigErr << 16
+    double *vw, *vz1, *vzn; int* vka; int vw_stride;
     // Lagrange form of the 3-point time polynomial (interpolation_module.f90:70-107),
     // LW[v][t] = weight of hydro record t (b,c,f) at internal time ix(v), with the p == 1
     // triplet (b,b,c) folded in; LW4 = (LW[0] + 4 LW[1] + LW[2]) / 6; LWz = raw weights at ix(2)

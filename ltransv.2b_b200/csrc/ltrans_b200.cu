@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 #include "lt_step2.cuh"
+#include "lt_vturb.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 // ------------------------------------------------------------------ kernels --
@@ -59,6 +60,36 @@ __global__ void __launch_bounds__(LT_BLK_VT, LT_MIN_VT) k_vturb(const __grid_con
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n < D.n) vturb_particle<T, PH>(D, n);
+}
+// VTurb as fit + walk (lt_vturb.cuh): k_vbuild spreads the 32 lanes of a warp over ONE particle's water
+// column at a time (shared-memory scratch per warp, no block-level synchronisation), k_vwalk is one
+// thread per particle.
+#ifndef LT_BLK_VB
+#define LT_BLK_VB 128
+#endif
+#ifndef LT_MIN_VB
+#define LT_MIN_VB 5
+#endif
+#ifndef LT_BLK_VW
+#define LT_BLK_VW 256
+#endif
+#ifndef LT_MIN_VW
+#define LT_MIN_VW 3
+#endif
+template <class T, int PH>
+__global__ void __launch_bounds__(LT_BLK_VB, LT_MIN_VB) k_vbuild(const __grid_constant__ LtDev D, int base, int count)
+{
+    extern __shared__ double vb_smem[];
+    const int wib = threadIdx.x >> 5;
+    const int warp_first = base + (blockIdx.x * (LT_BLK_VB / 32) + wib) * 32;
+    if (warp_first >= base + count) return;
+    vbuild_warp<T, PH>(D, vb_smem + (size_t)wib * vb_smem_doubles(D.P.ws), warp_first, base, count);
+}
+template <class T, int PH>
+__global__ void __launch_bounds__(LT_BLK_VW, LT_MIN_VW) k_vwalk(const __grid_constant__ LtDev D, int base, int count)
+{
+    const int n = base + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < base + count) vwalk_particle<T, PH>(D, n, base);
 }
 template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_FIN, LT_MIN_FIN) k_finish(const __grid_constant__ LtDev D)
@@ -301,6 +332,8 @@ struct ltgpu_ctx {
     void* pend_host[2] = {nullptr, nullptr}; size_t pend_bytes[2] = {0, 0};
     int key_bits = 32;
     long long sorts = 0;
+    // VTurb scratch (one chunk of particles between k_vbuild and k_vwalk)
+    int vt_chunk = 0; bool vt_legacy = false;
     // optional per-kernel timing (ltgpu_kernel_times)
     bool timing = false; cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; float tacc[4] = {0, 0, 0, 0}; long long tcount = 0;
 };
@@ -559,6 +592,42 @@ static int32_t fetch_flush(ltgpu_ctx* ctx)
     return LTGPU_OK;
 }
 
+// The launches of one internal step on the compute stream; T = field storage type, PH = ring phase.
+template <class T, int PH>
+static int32_t launch_step(ltgpu_ctx* ctx)
+{
+    const LtDev& D = ctx->D;
+    cudaStream_t st = ctx->compute;
+    const bool vt = ctx->prm.VTurbOn != 0;
+    if (ctx->timing) cudaEventRecord(ctx->tev[0], st);
+    k_advect<T, PH><<<(D.n + LT_BLK_ADV - 1) / LT_BLK_ADV, LT_BLK_ADV, 0, st>>>(D);
+    ctx->launches++;
+    if (ctx->timing) cudaEventRecord(ctx->tev[1], st);
+    if (vt && ctx->vt_legacy) {
+        k_vturb<T, PH><<<(D.n + LT_BLK_VT - 1) / LT_BLK_VT, LT_BLK_VT, 0, st>>>(D);
+        ctx->launches++;
+    } else if (vt) {
+        const size_t smem = sizeof(double) * (size_t)vb_smem_doubles(ctx->prm.ws) * (LT_BLK_VB / 32);
+        CK(cudaFuncSetAttribute(k_vbuild<T, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    // per device and function
+        for (int base = 0; base < D.n; base += ctx->vt_chunk) {
+            const int count = std::min(ctx->vt_chunk, D.n - base);
+            k_vbuild<T, PH><<<(count + LT_BLK_VB - 1) / LT_BLK_VB, LT_BLK_VB, smem, st>>>(D, base, count);
+            k_vwalk<T, PH><<<(count + LT_BLK_VW - 1) / LT_BLK_VW, LT_BLK_VW, 0, st>>>(D, base, count);
+            ctx->launches += 2;
+        }
+    }
+    if (ctx->timing) cudaEventRecord(ctx->tev[2], st);
+    k_finish<T, PH><<<(D.n + LT_BLK_FIN - 1) / LT_BLK_FIN, LT_BLK_FIN, 0, st>>>(D);
+    ctx->launches++;
+    if (ctx->timing) {
+        cudaEventRecord(ctx->tev[3], st);
+        cudaEventSynchronize(ctx->tev[3]);
+        for (int k = 0; k < 3; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ctx->tev[k], ctx->tev[k + 1]); ctx->tacc[k] += ms; }
+        ctx->tcount++;
+    }
+    return LTGPU_OK;
+}
+
 // Move the device event log to the host and recycle it.  Called at the library's synchronisation
 // points (ltgpu_sync, ltgpu_drain_events) with the compute stream idle, so the log only has to
 // hold the events of the steps queued between two of them; what did not fit is counted in
@@ -619,6 +688,7 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     ctx->sort_on = !(so && so[0] == '0');
     { const char* se = getenv("LTGPU_SORT_EVERY"); if (se && atoi(se) > 0) ctx->sort_every = atoi(se); }
     { const char* sm = getenv("LTGPU_SORT_MODE"); ctx->sort_mode = sm ? std::max(0, std::min(127, atoi(sm))) : 32; }
+    { const char* vl = getenv("LTGPU_VTURB_LEGACY"); ctx->vt_legacy = vl && vl[0] == '1'; }     // round-1 fused k_vturb (A/B only)
     { const char* ec = getenv("LTGPU_EVCAP"); ctx->evcap = ec && atoi(ec) > 0 ? atoi(ec) : 0; }   // 0: sized by set_particles
     *out = ctx;
     return LTGPU_OK;
@@ -898,6 +968,14 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
         CK(cudaMallocHost(&ctx->h_out[b], sizeof(double) * N));
         CK(cudaEventCreateWithFlags(&ctx->out_done[b], cudaEventDisableTiming));
     }
+    if (ctx->prm.VTurbOn && !ctx->vt_legacy) {
+        int chunk = 1 << 21;
+        { const char* vc = getenv("LTGPU_VTURB_CHUNK"); if (vc && atoi(vc) > 0) chunk = atoi(vc); }
+        chunk = std::min((n + 31) / 32 * 32, (chunk + 31) / 32 * 32);
+        ctx->vt_chunk = chunk; D.vw_stride = chunk;
+        TRY(dalloc(ctx, &D.vw, (size_t)3 * VW * chunk)); TRY(dalloc(ctx, &D.vz1, (size_t)chunk)); TRY(dalloc(ctx, &D.vzn, (size_t)chunk));
+        TRY(dalloc(ctx, &D.vka, (size_t)chunk));
+    }
     k_iota<<<(n + 255) / 256, 256, 0, ctx->compute>>>(ctx->d_pid, n);
     D.pid = ctx->d_pid;
     {
@@ -1023,21 +1101,15 @@ int32_t ltgpu_step(ltgpu_ctx* ctx, int32_t p, int32_t it)
         for (int t = 0; t < 3; ++t) D.LW4[t] = (D.LW[0][t] + 4.0 * D.LW[1][t] + D.LW[2][t]) / 6.0;
     }
     {
-        const bool vt = ctx->prm.VTurbOn != 0;
-        cudaStream_t st = ctx->compute;
-#define LT_LAUNCH(T, PH) do { if (ctx->timing) cudaEventRecord(ctx->tev[0], st); \
-                              k_advect<T, PH><<<(D.n + LT_BLK_ADV - 1) / LT_BLK_ADV, LT_BLK_ADV, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[1], st); \
-                              if (vt) k_vturb<T, PH><<<(D.n + LT_BLK_VT - 1) / LT_BLK_VT, LT_BLK_VT, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[2], st); \
-                              k_finish<T, PH><<<(D.n + LT_BLK_FIN - 1) / LT_BLK_FIN, LT_BLK_FIN, 0, st>>>(D); if (ctx->timing) cudaEventRecord(ctx->tev[3], st); } while (0)
-#define LT_LAUNCH_T(T) do { switch (D.sb) { case 0: LT_LAUNCH(T, 0); break; case 1: LT_LAUNCH(T, 1); break; \
-                                            case 2: LT_LAUNCH(T, 2); break; default: LT_LAUNCH(T, 3); break; } } while (0)
-        if (ctx->esz == 4) LT_LAUNCH_T(float); else LT_LAUNCH_T(double);
-        ctx->launches += vt ? 3 : 2;
-        if (ctx->timing) {
-            cudaEventSynchronize(ctx->tev[3]);
-            for (int k = 0; k < 3; ++k) { float ms = 0; cudaEventElapsedTime(&ms, ctx->tev[k], ctx->tev[k + 1]); ctx->tacc[k] += ms; }
-            ctx->tcount++;
+        int32_t rc = LTGPU_OK;
+        if (ctx->esz == 4) {
+            switch (D.sb) { case 0: rc = launch_step<float, 0>(ctx); break; case 1: rc = launch_step<float, 1>(ctx); break;
+                            case 2: rc = launch_step<float, 2>(ctx); break; default: rc = launch_step<float, 3>(ctx); break; }
+        } else {
+            switch (D.sb) { case 0: rc = launch_step<double, 0>(ctx); break; case 1: rc = launch_step<double, 1>(ctx); break;
+                            case 2: rc = launch_step<double, 2>(ctx); break; default: rc = launch_step<double, 3>(ctx); break; }
         }
+        if (rc) return rc;
     }
     CK(cudaGetLastError());
     ctx->last_ix3 = D.ix[2];

@@ -1,0 +1,581 @@
+"""Second, independent restatement of the reference's LEAF numerics, in plain Python floats.
+
+TEST INFRASTRUCTURE ONLY (same rule as the rest of oracle/).  Purpose (SURVEY.md 8c,
+mitigation 1): the Fortran cannot be compiled here, so the C oracle (ora_leaf.c) is pinned by a
+differential test against a second reading of the same Fortran lines, written separately in a
+different language and shape.  Python floats are IEEE doubles, `math.exp / sqrt` are the C
+library's, and the oracle is built with -ffp-contract=off, so the two must agree BIT FOR BIT
+(tests/test_oracle_differential.py asserts equality, not closeness, wherever both sides follow
+the reference's operation order).
+
+Every function cites the reference lines it follows (/root/reference/Model/).
+"""
+import math
+
+SBIG = 85.0
+EPS_RTOL = 200.0 * 2.0 ** -53      # tension_module.f90:433-439: RTOL halves until 1 + RTOL <= 1, then x 200
+
+
+# ---------------------------------------------------------------- interpolation_module.f90
+def linint(xa, ya, x):
+    """interpolation_module.f90:25-59 -> (y, m)"""
+    jlo, jhi = 1, len(xa)
+    while True:
+        k = (jhi + jlo) // 2
+        if xa[k - 1] > x:
+            jhi = k
+        else:
+            jlo = k
+        if jhi - jlo == 1:
+            break
+    m = (ya[jlo - 1] - ya[jhi - 1]) / (xa[jlo - 1] - xa[jhi - 1])
+    b = ya[jlo - 1] - m * xa[jlo - 1]
+    return m * x + b, m
+
+
+def polintd(xa, ya, x):
+    """interpolation_module.f90:70-107 (n = 3)"""
+    ns, dif = 1, abs(x - xa[0])
+    for i in range(1, 4):
+        dift = abs(x - xa[i - 1])
+        if dift < dif:
+            ns, dif = i, dift
+    c = (xa[1] - x) * ((ya[2] - ya[1]) / (xa[1] - xa[2]))
+    c = c - (xa[1] - x) * ((ya[1] - ya[0]) / (xa[0] - xa[1]))
+    c = c / (xa[0] - xa[2])
+    if ns == 3:
+        a = (ya[2] - ya[1]) / (xa[1] - xa[2]); b = xa[2] - x
+    else:
+        a = (ya[1] - ya[0]) / (xa[0] - xa[1]); b = xa[0] - x
+    return ya[ns - 1] + (xa[ns - 1] - x) * a + b * c
+
+
+# ---------------------------------------------------------------------- tension_module.f90
+_P = (-3.51754964808151394800e5, -1.15614435765005216044e4, -1.63725857525983828727e2, -7.89474443963537015605e-1)
+_Q = (-2.11052978884890840399e6, 3.61578279834431989373e4, -2.77711081420602794433e2, 1.0)
+
+
+def snhcsh(x):
+    """tension_module.f90:784-850 -> (sinh x - x, cosh x - 1, cosh x - 1 - x^2/2)"""
+    ax = abs(x); xs = ax * ax
+    if ax <= 0.5:
+        xc = x * xs
+        p = ((_P[3] * xs + _P[2]) * xs + _P[1]) * xs + _P[0]
+        q = ((_Q[3] * xs + _Q[2]) * xs + _Q[1]) * xs + _Q[0]
+        sinhm = xc * (p / q)
+        xsd4 = 0.25 * xs; xsd2 = xsd4 + xsd4
+        p = ((_P[3] * xsd4 + _P[2]) * xsd4 + _P[1]) * xsd4 + _P[0]
+        q = ((_Q[3] * xsd4 + _Q[2]) * xsd4 + _Q[1]) * xsd4 + _Q[0]
+        f = xsd4 * (p / q)
+        coshmm = xsd2 * f * (f + 2.0)
+        coshm = coshmm + xsd2
+    else:
+        expx = math.exp(ax)
+        sinhm = -(((1.0 / expx + ax) + ax) - expx) / 2.0
+        if x < 0.0:
+            sinhm = -sinhm
+        coshm = ((1.0 / expx - 2.0) + expx) / 2.0
+        coshmm = coshm - xs / 2.0
+    return sinhm, coshm, coshmm
+
+
+def _sign(a, b):
+    return abs(a) if (b > 0.0 or (b == 0.0 and math.copysign(1.0, b) > 0)) else -abs(a)
+
+
+def ypc1(x, y):
+    """tension_module.f90:852-978 -> (yp, ier)"""
+    n = len(x); nm1 = n - 1
+    yp = [0.0] * n
+    dxi = x[1] - x[0]
+    if dxi <= 0.0:
+        return yp, 2
+    si = (y[1] - y[0]) / dxi
+    if nm1 == 1:
+        return [si, si], 0
+    dx2 = x[2] - x[1]
+    if dx2 <= 0.0:
+        return yp, 3
+    s2 = (y[2] - y[1]) / dx2
+    t = si + dxi * (si - s2) / (dxi + dx2)
+    yp[0] = min(max(0.0, t), 3.0 * si) if si >= 0.0 else max(min(0.0, t), 3.0 * si)
+    sim1 = dxim1 = 0.0
+    for i in range(2, nm1 + 1):
+        dxim1 = dxi
+        dxi = x[i] - x[i - 1]
+        if dxi <= 0.0:
+            return yp, i + 1
+        sim1 = si
+        si = (y[i] - y[i - 1]) / dxi
+        t = (dxim1 * si + dxi * sim1) / (dxim1 + dxi)
+        asim1, asi = abs(sim1), abs(si)
+        sgn = _sign(1.0, si)
+        if asim1 > asi:
+            sgn = _sign(1.0, sim1)
+        if sgn > 0.0:
+            yp[i - 1] = min(max(0.0, t), 3.0 * min(asim1, asi))
+        else:
+            yp[i - 1] = max(min(0.0, t), -3.0 * min(asim1, asi))
+    t = si + dxi * (si - sim1) / (dxim1 + dxi)
+    yp[n - 1] = min(max(0.0, t), 3.0 * si) if si >= 0.0 else max(min(0.0, t), 3.0 * si)
+    return yp, 0
+
+
+def convexity_newton(T, nit_cap=10000):
+    """The Newton loop of SIGS' convexity branch (tension_module.f90:520-579) for one interval with
+    T = max(D1/D2, D2/D1) > 2.  -> (SIG, failed): failed <=> NIT > 10000, the reference's SigErr."""
+    rtol, ftol = EPS_RTOL, 0.0
+    tp1 = T + 1.0
+    sig = math.sqrt(10.0 * T - 20.0)
+    nit = 0
+    while True:
+        if sig <= 0.5:
+            sinhm, coshm, coshmm = snhcsh(sig)
+            t1 = coshm / sinhm
+            fp = t1 + sig * (sig / sinhm - t1 * t1 + 1.0)
+        else:
+            ems = math.exp(-sig)
+            ssm = 1.0 - ems * (ems + sig + sig)
+            t1 = (1.0 - ems) * (1.0 - ems) / ssm
+            fp = t1 + sig * (2.0 * sig * ems / ssm - t1 * t1 + 1.0)
+        f = sig * t1 - tp1
+        nit += 1
+        if nit > nit_cap:
+            return sig, True
+        if fp <= 0.0:
+            return sig, False
+        dsig = -f / fp
+        if abs(dsig) <= rtol * sig or (0.0 <= f <= ftol) or abs(f) <= rtol:
+            return sig, False
+        sig = sig + dsig
+
+
+def sigs(x, y, yp, secant_cap=100000):
+    """tension_module.f90:314-782 with TOL = 0 -> (sigma, sigerr).  CONT starts .TRUE. in every
+    interval (ledger 18: uninitialised in the reference on the SIG <= .5 secant branch).  The
+    secant loop has no cap in the reference; `secant_cap` passes (or a NaN residual, which can never
+    leave the loop) are reported as SigErr, as in the C oracle."""
+    n = len(x); nm1 = n - 1
+    sigma = [0.0] * n
+    rtol, ftol = EPS_RTOL, 0.0
+    for i in range(nm1):
+        dx = x[i + 1] - x[i]
+        if dx <= 0.0:
+            return sigma, 0
+        s1, s2 = yp[i], yp[i + 1]
+        s = (y[i + 1] - y[i]) / dx
+        d1 = s - s1; d2 = s2 - s; d1d2 = d1 * d2
+        if (d1d2 == 0.0 and s1 != s2) or (s == 0.0 and s1 * s2 > 0.0):
+            sigma[i] = SBIG
+            continue
+        if d1d2 >= 0.0:
+            if d1d2 == 0.0:
+                continue
+            t = max(d1 / d2, d2 / d1)
+            if t <= 2.0:
+                continue
+            sig, failed = convexity_newton(t)
+            if failed:
+                return sigma, 1                      # RETURN: the remaining intervals keep SIGMA = 0
+            sig = min(sig, SBIG)
+            if sig > 0.0:
+                sigma[i] = sig
+            continue
+        # monotonicity, :638-760
+        if s1 * s < 0.0 or s2 * s < 0.0:
+            continue
+        t0 = 3.0 * s - s1 - s2
+        d0 = t0 * t0 - s1 * s2
+        if d0 <= 0.0 or s * t0 >= 0.0:
+            continue
+        sgn = _sign(1.0, s)
+        sig = SBIG
+        fmax = sgn * (sig * s - s1 - s2) / (sig - 2.0)
+        if fmax <= 0.0:
+            sigma[i] = SBIG
+            continue
+        stol = rtol * sig
+        f = fmax
+        f0 = sgn * d0 / (3.0 * (d1 - d2))
+        fneg = f0
+        dsig = sig; dmax = sig
+        d1pd2 = d1 + d2
+        nit = 0
+        cont = True
+        a = e = c1 = c2 = 0.0
+        err = False
+        while True:
+            dsig = -f * dsig / (f - f0)
+            if abs(dsig) > abs(dmax) or dsig * dmax > 0.0:
+                dsig = dmax; f0 = fneg
+                nit += 1
+                if nit > secant_cap:
+                    err = True; break
+                continue
+            if abs(dsig) < stol / 2.0:
+                dsig = -_sign(stol / 2.0, dmax)
+            sig = sig + dsig
+            f0 = f
+            if sig <= 0.5:
+                sinhm, coshm, coshmm = snhcsh(sig)
+                c1 = sig * coshm * d2 - sinhm * d1pd2
+                c2 = sig * (sinhm + sig) * d2 - coshm * d1pd2
+                a = c2 - c1
+                e = sig * sinhm - coshmm - coshmm
+            else:
+                ems = math.exp(-sig); ems2 = ems + ems; tm = 1.0 - ems
+                ssinh = tm * (1.0 + ems); ssm = ssinh - sig * ems2; scm = tm * tm
+                c1 = sig * scm * d2 - ssm * d1pd2
+                c2 = sig * ssinh * d2 - scm * d1pd2
+                f = fmax
+                cont = True
+                if c1 * (sig * scm * d1 - ssm * d1pd2) >= 0.0:
+                    cont = False
+                if cont:
+                    a = ems2 * (sig * tm * d2 + (tm - sig) * d1pd2)
+                if a * (c2 + c1) < 0.0:
+                    cont = False
+                if cont:
+                    e = sig * ssinh - scm - scm
+            if cont:
+                arg = a * (c2 + c1)
+                root = math.sqrt(arg) if arg >= 0.0 else float("nan")
+                f = (sgn * (e * s2 - c2) + root) / e
+            nit += 1
+            if nit > secant_cap:
+                err = True; break
+            stol = rtol * sig
+            if abs(dmax) <= stol or (0.0 <= f <= ftol) or abs(f) <= rtol:
+                break
+            if f != f:
+                err = True; break
+            dmax = dmax + dsig
+            if f0 * f > 0.0 and abs(f) >= abs(f0):
+                dsig = dmax; f0 = fneg
+                continue
+            if f0 * f <= 0.0:
+                t1, t2 = dmax, fneg
+                dmax = dsig; fneg = f0
+                if abs(dsig) > abs(t1) and abs(f) < abs(t2):
+                    dsig = t1; f0 = t2
+        if err:
+            return sigma, 1
+        sig = min(sig, SBIG)
+        if sig > 0.0:
+            sigma[i] = sig
+    return sigma, 0
+
+
+def tspsi(x, y):
+    """tension_module.f90:231-312 -> (yp, sigma, ier, sigerr)"""
+    if len(x) < 2:
+        return [], [], -1, 0
+    yp, ierr = ypc1(x, y)
+    if ierr != 0:
+        return yp, [0.0] * len(x), -4, 0
+    sigma, sigerr = sigs(x, y, yp)
+    return yp, sigma, 0, sigerr
+
+
+def intrvl(t, x):
+    """tension_module.f90:1287-1354 without the SAVEd cache (ledger 20): 1-based I with X(I) <= T < X(I+1)"""
+    il, ih = 1, len(x)
+    while ih > il + 1:
+        k = (il + ih) // 2
+        if t < x[k - 1]:
+            ih = k
+        else:
+            il = k
+    return il
+
+
+def _interval(t, x):
+    n = len(x)
+    if t < x[0]:
+        return 1
+    if t > x[n - 1]:
+        return n - 1
+    return intrvl(t, x)
+
+
+def hval(t, x, y, yp, sigma):
+    """tension_module.f90:1002-1119"""
+    i = _interval(t, x) - 1
+    dx = x[i + 1] - x[i]
+    u = t - x[i]
+    b2 = u / dx; b1 = 1.0 - b2
+    y1 = y[i]; s1 = yp[i]
+    s = (y[i + 1] - y1) / dx
+    d1 = s - s1; d2 = yp[i + 1] - s
+    sig = abs(sigma[i])
+    if sig < 1.0e-9:
+        return y1 + u * (s1 + b2 * (d1 + b1 * (d1 - d2)))
+    if sig <= 0.5:
+        sb2 = sig * b2
+        sm, cm, cmm = snhcsh(sig)
+        sm2, cm2, _ = snhcsh(sb2)
+        e = sig * sm - cmm - cmm
+        return y1 + s1 * u + dx * ((cm * sm2 - sm * cm2) * (d1 + d2) + sig * (cm * cm2 - (sm + sig) * sm2) * d1) / (sig * e)
+    sb1 = sig * b1; sb2 = sig - sb1
+    if -sb1 > SBIG or -sb2 > SBIG:
+        return y1 + s * u
+    e1 = math.exp(-sb1); e2 = math.exp(-sb2); ems = e1 * e2
+    tm = 1.0 - ems; ts = tm * tm; tp = 1.0 + ems
+    e = tm * (sig * tp - tm - tm)
+    return y1 + s * u + dx * (tm * (tp - e1 - e2) * (d1 + d2) + sig * ((e2 + ems * (e1 - 2.0) - b1 * ts) * d1
+                                                                           + (e1 + ems * (e2 - 2.0) - b2 * ts) * d2)) / (sig * e)
+
+
+def hpval(t, x, y, yp, sigma):
+    """tension_module.f90:1122-1251"""
+    i = _interval(t, x) - 1
+    dx = x[i + 1] - x[i]
+    b1 = (x[i + 1] - t) / dx; b2 = 1.0 - b1
+    s1 = yp[i]
+    s = (y[i + 1] - y[i]) / dx
+    d1 = s - s1; d2 = yp[i + 1] - s
+    sig = abs(sigma[i])
+    if sig < 1.0e-9:
+        return s1 + b2 * (d1 + d2 - 3.0 * b1 * (d2 - d1))
+    if sig <= 0.5:
+        sb2 = sig * b2
+        sm, cm, cmm = snhcsh(sig)
+        sm2, cm2, _ = snhcsh(sb2)
+        sinh2 = sm2 + sb2
+        e = sig * sm - cmm - cmm
+        return s1 + ((cm * cm2 - sm * sinh2) * (d1 + d2) + sig * (cm * sinh2 - (sm + sig) * cm2) * d1) / e
+    sb1 = sig * b1; sb2 = sig - sb1
+    if -sb1 > SBIG or -sb2 > SBIG:
+        return s
+    e1 = math.exp(-sb1); e2 = math.exp(-sb2); ems = e1 * e2
+    tm = 1.0 - ems
+    e = tm * (sig * (1.0 + ems) - tm - tm)
+    return s + (tm * ((e2 - e1) * (d1 + d2) + tm * (d1 - d2)) + sig * ((e1 * ems - e2) * d1 + (e1 - e2 * ems) * d2)) / e
+
+
+# ---------------------------------------------------------------------- gridcell_module.f90
+def gridcell(ex, ey, X, Y):
+    """gridcell_module.f90:26-257 for ONE element (checkele form): True <=> triangle /= 0"""
+    if all(Y < v for v in ey) or all(Y > v for v in ey):
+        return False
+    if all(X < v for v in ex) or all(X > v for v in ex):
+        return False
+    for k in range(4):
+        if X == ex[k] and Y == ey[k]:
+            return True
+    for a, b in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)):           # :72-143, in this order
+        if ey[a] == ey[b] and Y == ey[a]:
+            return (ex[a] > ex[b] and ex[b] < X < ex[a]) or (ex[b] > ex[a] and ex[a] < X < ex[b])
+    if Y in (ey[0], ey[1], ey[2], ey[3]):                                   # :147-176
+        if Y == max(ey) or Y == min(ey):
+            return False
+    hit = False
+    counter = [0, 0, 0, 0]
+    for p in range(4):                                                      # :178-243
+        bx1, by1, bx2, by2 = ex[p], ey[p], ex[(p + 1) % 4], ey[(p + 1) % 4]
+        if X <= bx1 or X <= bx2:
+            if (by1 > by2 and by2 <= Y <= by1) or (by2 > by1 and by1 <= Y <= by2):
+                if bx1 == bx2:
+                    if X == bx1:
+                        hit = True; break
+                    counter[p] = 0 if Y == by2 else 1
+                else:
+                    slope = (by1 - by2) / (bx1 - bx2)
+                    xi = (Y - by1 + (slope * bx1)) / slope
+                    if xi > X:
+                        counter[p] = 0 if Y == by2 else 1
+                    if xi == X:
+                        hit = True; break
+    return hit or (sum(counter) % 2 != 0)
+
+
+# -------------------------------------------------------------- point_in_polygon_module.f90
+def inpoly(x, y, e, onin=None):
+    """point_in_polygon_module.f90:25-167; e = [(x, y), ...] closed polygon (first point repeated)"""
+    n = len(e)
+    onout = (not onin) if onin is not None else False
+    hilo = [0] * (n + 2)                      # 1-based, hilo[0] stands for hilo(0) (never reached: `first`)
+    on = False
+    for i in range(1, n + 1):
+        ex_, ey_ = e[i - 1]
+        if ey_ > y:
+            hilo[i] = 1
+        if ey_ < y:
+            hilo[i] = -1
+        if ey_ == y and ex_ > x:
+            on = True
+        if ex_ == x and ey_ == y:
+            return not onout
+    crossed = 0
+    if on:
+        first = True
+        i = 1
+        while True:
+            if i > n:
+                break
+            if hilo[i] == 0 and e[i - 1][0] > x:
+                if first:
+                    i += 1
+                    continue
+                if hilo[i - 1] == 0:
+                    return not onout
+                j = 1
+                while True:
+                    if i + j == n + 1:
+                        j = 2 - i
+                    if hilo[i + j] != 0:
+                        break
+                    if e[i + j - 1][0] < x:
+                        return not onout
+                    j += 1
+                if hilo[i - 1] + hilo[i + j] == 0:
+                    crossed += 1
+                if j < 0:
+                    break
+                i = i + j
+            first = False
+            i += 1
+    for i in range(1, n):
+        ax, ay = e[i - 1]; bx, by = e[i]
+        if ax <= x and bx <= x:
+            continue
+        if ay <= y and by <= y:
+            continue
+        if ay >= y and by >= y:
+            continue
+        if ax > x and bx > x:
+            crossed += 1
+            continue
+        m = (by - ay) / (bx - ax)
+        b = ay - m * ax
+        ix = (y - b) / m
+        if ix == x:
+            return not onout
+        if ix > x:
+            crossed += 1
+    return crossed % 2 != 0
+
+
+# ------------------------------------------------------------------------ boundary_module.f90
+def _sq(v):
+    return v * v
+
+
+def intersect_reflect(bnd, land, Xpos, Ypos, nXpos, nYpos, skipbound=0):
+    """boundary_module.f90:1620-1902.  bnd = [(x1, y1, x2, y2), ...]; skipbound 1-based (0 = none).
+    -> (intersectf, fiX, fiY, frX, frY, skipbound, isWater).  rPxyz keeps its previous value when
+    dist1 == dist2 (ledger 19): it starts undefined in the reference, here as NaN."""
+    fiX = fiY = frX = frY = -999999.0
+    dtest = 999999.0
+    isWater = False
+    intersectf = 0
+    skipi = skipbound
+    xhigh, xlow = (Xpos, nXpos) if Xpos >= nXpos else (nXpos, Xpos)
+    yhigh, ylow = (Ypos, nYpos) if Ypos >= nYpos else (nYpos, Ypos)
+    rPx = rPy = float("nan")
+    ix = iy = float("nan")
+    Mbc = 0.0
+    for i in range(1, len(bnd) + 1):
+        if i == skipbound:
+            continue
+        intersect = 0
+        bcx1, bcy1, bcx2, bcy2 = bnd[i - 1]
+        if ((bcx1 > xhigh and bcx2 > xhigh) or (bcx1 < xlow and bcx2 < xlow) or
+                (bcy1 > yhigh and bcy2 > yhigh) or (bcy1 < ylow and bcy2 < ylow)):
+            continue
+        bxhigh, bxlow = (bcx1, bcx2) if bcx1 >= bcx2 else (bcx2, bcx1)
+        byhigh, bylow = (bcy1, bcy2) if bcy1 >= bcy2 else (bcy2, bcy1)
+
+        def inside():
+            return (xlow <= ix <= xhigh and ylow <= iy <= yhigh and bxlow <= ix <= bxhigh and bylow <= iy <= byhigh)
+
+        def pick(rx1, ry1, rx2, ry2):
+            nonlocal rPx, rPy
+            dist1 = math.sqrt(_sq(ix - rx1) + _sq(iy - ry1))
+            dist2 = math.sqrt(_sq(ix - rx2) + _sq(iy - ry2))
+            if dist1 < dist2:
+                rPx, rPy = rx1, ry1
+            elif dist1 > dist2:
+                rPx, rPy = rx2, ry2
+
+        def oblique():
+            distBC = math.sqrt(_sq(bcx1 - bcx2) + _sq(bcy1 - bcy2))
+            crossk = ((nXpos - bcx1) * (bcy2 - bcy1)) - ((bcx2 - bcx1) * (nYpos - bcy1))
+            dPBC = math.sqrt(_sq(crossk)) / distBC
+            mP = -1.0 / Mbc
+            bP = nYpos - mP * nXpos
+            r = math.sqrt(_sq(2.0 * dPBC) / (1.0 + _sq(mP)))
+            rx1 = r + nXpos; ry1 = mP * rx1 + bP
+            rx2 = r * -1.0 + nXpos; ry2 = mP * rx2 + bP
+            pick(rx1, ry1, rx2, ry2)
+
+        if bcx1 == bcx2 or nXpos == Xpos:
+            if bcx1 == bcx2 and nXpos == Xpos:
+                continue
+            if bcx1 == bcx2 and nYpos == Ypos:
+                ix, iy = bcx1, nYpos
+                if inside():
+                    dPBC = math.sqrt(_sq(ix - nXpos) + _sq(iy - nYpos))
+                    pick(nXpos + 2.0 * dPBC, nYpos, nXpos - 2.0 * dPBC, nYpos)
+                    intersect = 1
+            elif nXpos == Xpos and bcy1 == bcy2:
+                ix, iy = nXpos, bcy1
+                if inside():
+                    dPBC = math.sqrt(_sq(ix - nXpos) + _sq(iy - nYpos))
+                    pick(nXpos, nYpos + 2.0 * dPBC, nXpos, nYpos - 2.0 * dPBC)
+                    intersect = 1
+            elif bcx1 == bcx2 and nYpos != Ypos:
+                Mp = (nYpos - Ypos) / (nXpos - Xpos)
+                Bp = Ypos - Mp * Xpos
+                ix = bcx1; iy = Mp * ix + Bp
+                if inside():
+                    dPBC = nXpos - ix
+                    pick(nXpos + 2.0 * dPBC, nYpos, nXpos - 2.0 * dPBC, nYpos)
+                    intersect = 1
+            elif nXpos == Xpos and bcy1 != bcy2:
+                Mbc = (bcy2 - bcy1) / (bcx2 - bcx1)
+                Bbc = bcy2 - Mbc * bcx2
+                ix = nXpos; iy = Mbc * ix + Bbc
+                if inside():
+                    oblique()
+                    intersect = 1
+        else:
+            Mbc = (bcy2 - bcy1) / (bcx2 - bcx1)
+            Bbc = bcy2 - Mbc * bcx2
+            Mp = (nYpos - Ypos) / (nXpos - Xpos)
+            Bp = Ypos - Mp * Xpos
+            ix = (Bbc - Bp) / (Mp - Mbc)
+            iy = Mp * ix + Bp
+            if Mbc == 0.0:
+                iy = byhigh
+            if inside():
+                if Mbc == 0.0:
+                    dPBC = nYpos - bcy1
+                    pick(nXpos, nYpos + 2.0 * dPBC, nXpos, nYpos - 2.0 * dPBC)
+                else:
+                    oblique()
+                intersect = 1
+        d_P = math.sqrt(_sq(Xpos - ix) + _sq(Ypos - iy))
+        if intersect == 1 and d_P < dtest:
+            fiX, fiY, frX, frY = ix, iy, rPx, rPy
+            intersectf = 1
+            dtest = d_P
+            skipi = i
+            isWater = not land[i - 1]
+    return intersectf, fiX, fiY, frX, frY, skipi, isWater
+
+
+# -------------------------------------------------------------------- hydrodynamic_module.f90
+def slevel(zeta, depth, sc, cs, hc32, vtransform):
+    """getSlevel / getWlevel (hydrodynamic_module.f90:2691-2777); hc is REAL(4) (ledger 4),
+    passed here already widened from float32"""
+    h = -1.0 * depth
+    if vtransform == 1:
+        S = hc32 * sc + (h - hc32) * cs
+        return S + zeta * (1.0 + S / h)
+    if vtransform == 2:
+        S = (hc32 * sc + h * cs) / (hc32 + h)
+        return zeta + (zeta + h) * S
+    if vtransform == 3:
+        return zeta * (1.0 + sc) + hc32 * sc + (h - hc32) * cs
+    raise ValueError("Illegal Vtransform number")

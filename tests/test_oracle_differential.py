@@ -1,0 +1,252 @@
+"""Differential pin of the C oracle (oracle/ora_leaf.c, ora_step.c leaf exports) against the second,
+independent restatement of the same Fortran lines (oracle/np_leaf.py), SURVEY.md 8c mitigation 1.
+
+Both sides follow the reference's operation order in IEEE double without FMA contraction and call
+the same libm, so the comparison is for EQUALITY of bits (NaN == NaN), not closeness: a
+transcription slip in either reading shows up as a hard failure on the first input that reaches the
+mistaken line.  Inputs come from hypothesis (seeded, derandomised) plus constructed on-edge /
+on-vertex / in-band cases that random sampling would never hit.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+from oracle import np_leaf as NL
+from oracle.oracle import leaf, dptr
+
+L = leaf()
+SET = dict(max_examples=300, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+fin = st.floats(min_value=-1e6, max_value=1e6, allow_nan=False, allow_infinity=False, width=64)
+
+
+def same(a, b):
+    return a == b or (a != a and b != b)
+
+
+def arr(v):
+    return np.ascontiguousarray(v, dtype=np.float64)
+
+
+# ---------------------------------------------------------------- polintd / linint
+@settings(**SET)
+@given(st.integers(0, 40), st.lists(fin, min_size=3, max_size=3), st.floats(-0.5, 2.5))
+def test_polintd_bit_equal(p, ya, frac):
+    xa = [p * 3600.0, (p + 1) * 3600.0, (p + 2) * 3600.0]          # ex(1..3), LTRANS.f90:568-571
+    x = xa[0] + frac * 3600.0
+    got = L.ora_polintd(dptr(arr(xa)), dptr(arr(ya)), x)
+    assert same(got, NL.polintd(xa, ya, x))
+
+
+@settings(**SET)
+@given(st.lists(st.floats(1e-3, 50.0), min_size=2, max_size=40), st.data())      # n >= 3: with n = 2 and x < xa(1) the reference's bisection never ends
+def test_linint_bit_equal(gaps, data):
+    xa = np.concatenate([[-30.0], -30.0 + np.cumsum(gaps)])
+    ya = arr(data.draw(st.lists(fin, min_size=len(xa), max_size=len(xa))))
+    x = data.draw(st.floats(float(xa[0]) - 5.0, float(xa[-1]) + 5.0))
+    y, m = C.c_double(), C.c_double()
+    L.ora_linint(dptr(xa), dptr(ya), len(xa), x, C.byref(y), C.byref(m))
+    wy, wm = NL.linint(list(xa), list(ya), x)
+    assert same(y.value, wy) and same(m.value, wm)
+
+
+# ---------------------------------------------------------------- SNHCSH, s-levels
+@settings(**SET)
+@given(st.one_of(st.floats(-6.0, 6.0), st.sampled_from([0.0, 0.5, -0.5, 0.5000000000000001, 1e-300, 85.0])))
+def test_snhcsh_bit_equal(x):
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    L.ora_snhcsh(x, C.byref(a), C.byref(b), C.byref(c))
+    w = NL.snhcsh(x)
+    assert same(a.value, w[0]) and same(b.value, w[1]) and same(c.value, w[2])
+
+
+@settings(**SET)
+@given(st.floats(-2.0, 2.0), st.floats(0.5, 4000.0), st.floats(-1.0, 0.0), st.floats(-1.0, 0.0), st.sampled_from([1, 2, 3]),
+       st.sampled_from([0.2, 5.0, 20.0, 250.0]))
+def test_slevel_bit_equal(zeta, h, sc, cs, vt, hc):
+    hc32 = float(np.float32(hc))                                     # hc is REAL(4), ledger 4
+    got = L.ora_slevel(zeta, -h, sc, cs, C.c_float(hc), vt)
+    assert same(got, NL.slevel(zeta, -h, sc, cs, hc32, vt))
+
+
+# ---------------------------------------------------------------- TSPSI / HVAL / HPVAL
+def _c_tspsi(x, y):
+    n = len(x)
+    yp, sg = np.zeros(n), np.zeros(n)
+    ier, se = C.c_int32(0), C.c_int32(0)
+    L.ora_tspsi(n, dptr(x), dptr(y), dptr(yp), dptr(sg), C.byref(ier), C.byref(se))
+    return yp, sg, ier.value, se.value
+
+
+def _check_spline(x, y, ts):
+    x, y = arr(x), arr(y)
+    yp, sg, ier, se = _c_tspsi(x, y)
+    wyp, wsg, wier, wse = NL.tspsi(list(x), list(y))
+    assert ier == wier and se == wse
+    assert all(same(a, b) for a, b in zip(yp, wyp)), (list(yp), wyp)
+    assert all(same(a, b) for a, b in zip(sg, wsg)), (list(sg), wsg)
+    if se == 0 and ier == 0:
+        e = C.c_int32(0)
+        for t in ts:
+            assert same(L.ora_hval(t, len(x), dptr(x), dptr(y), dptr(yp), dptr(sg), C.byref(e)), NL.hval(t, list(x), list(y), wyp, wsg))
+            assert same(L.ora_hpval(t, len(x), dptr(x), dptr(y), dptr(yp), dptr(sg), C.byref(e)), NL.hpval(t, list(x), list(y), wyp, wsg))
+    return se, sg
+
+
+@settings(**SET)
+@given(st.lists(st.floats(1e-2, 30.0), min_size=1, max_size=30), st.data())
+def test_tspsi_hval_hpval_bit_equal_random_data(gaps, data):
+    x = np.concatenate([[-25.0], -25.0 + np.cumsum(gaps)])
+    kind = data.draw(st.sampled_from(["noise", "monotone", "steps", "smooth"]))
+    r = np.array(data.draw(st.lists(st.floats(-1.0, 1.0), min_size=len(x), max_size=len(x))))
+    if kind == "noise":
+        y = r * 10.0
+    elif kind == "monotone":
+        y = np.cumsum(np.abs(r)) * 1e-3                              # exercises the monotonicity (secant) branch
+    elif kind == "steps":
+        y = np.round(r * 2.0)                                        # flats and jumps: SIGMA = SBIG cases, zero slopes
+    else:
+        y = 4e-3 * (x - x[0]) * (x[-1] - x) / max(1e-9, (x[-1] - x[0]) ** 2) + 1e-5 * r
+    ts = [float(x[0]) - 1.0, float(x[-1]) + 1.0] + [float(v) for v in x[:3]] + \
+         [float(x[0] + f * (x[-1] - x[0])) for f in (0.01, 0.37, 0.5, 0.93)]
+    _check_spline(x, y, ts)
+
+
+def test_tspsi_bit_equal_on_smooth_kh_like_profiles():
+    """KH-like columns: a parabola with wiggles on stretched knots, the shape VTurb fits"""
+    rng = np.random.default_rng(42)
+    for _ in range(800):
+        n = int(rng.integers(4, 90))
+        x = np.cumsum(rng.uniform(0.2, 1.0, n))
+        u = (x - x[0]) / (x[-1] - x[0])
+        y = 1e-5 + 4e-3 * 4 * u * (1 - u) * (0.8 + 0.2 * np.sin(7 * np.pi * u + rng.uniform(0, 6))) + 1e-6 * rng.normal(size=n) * rng.choice([0.0, 1.0])
+        _check_spline(x, y, [float(x[n // 2]) + 0.01, float(x[1]) - 0.05])
+
+
+def test_sigerr_verdict_bit_equal_on_a_scan_of_the_band():
+    """SIGS raises SigErr when its convexity Newton loop (tension:528-579) is still wandering after 10,000
+    iterations; the loop's verdict is a function of T = max(D1/D2, D2/D1) alone and fails for about one T in
+    a thousand between 2.025 and 2.03.  On uniform knots YPC1 gives the middle interval
+    of four knots T = (s3 - s2)/(s2 - s1) for chord slopes s1 < s2 < s3, so T can be aimed: both readings must
+    return the same verdict and the same tension factors for every T, and the scan must contain failures."""
+    rng = np.random.default_rng(7)
+    nfail = 0
+    for _ in range(12000):
+        T = rng.uniform(2.0249, 2.0320)
+        sc = 2.0 ** rng.integers(-20, 8)                                # exact scaling: varies the operands, not T
+        s1, s2 = 1.0, 2.0
+        s3 = s2 + T * (s2 - s1)
+        x = np.array([0.0, 1.0, 2.0, 3.0])
+        y = np.array([0.0, s1, s1 + s2, s1 + s2 + s3]) * sc
+        yp, sg, ier, se = _c_tspsi(x, y)
+        wyp, wsg, wier, wse = NL.tspsi(list(x), list(y))
+        assert (ier, se) == (wier, wse) and all(same(a, b) for a, b in zip(sg, wsg)) and all(same(a, b) for a, b in zip(yp, wyp))
+        d1, d2 = (y[2] - y[1]) - wyp[1], wyp[2] - (y[2] - y[1])
+        Tm = max(d1 / d2, d2 / d1)
+        assert abs(Tm - T) < 1e-9
+        sig, failed = NL.convexity_newton(Tm)
+        assert failed == bool(se)
+        nfail += se
+    assert nfail >= 3, nfail
+
+
+# ---------------------------------------------------------------- gridcell / inpoly
+def _quad(rng, integer):
+    c = rng.uniform(-5, 5, 2)
+    ang = np.sort(rng.uniform(0, 2 * np.pi, 4))[::-1]               # clockwise like the ROMS elements
+    r = rng.uniform(0.5, 3.0, 4)
+    ex, ey = c[0] + r * np.cos(ang), c[1] + r * np.sin(ang)
+    if integer:
+        ex, ey = np.round(ex), np.round(ey)
+    return arr(ex), arr(ey)
+
+
+def test_gridcell_bit_equal_incl_edges_and_vertices():
+    rng = np.random.default_rng(3)
+    n_on = 0
+    for it in range(6000):
+        ex, ey = _quad(rng, integer=it % 2 == 0)
+        mode = it % 5
+        if mode == 0:
+            X, Y = rng.uniform(-9, 9, 2)
+        elif mode == 1:
+            k = rng.integers(4); X, Y = ex[k], ey[k]                 # on a vertex
+        elif mode == 2:
+            k = rng.integers(4); f = rng.choice([0.25, 0.5, 0.75])   # on an edge (exact for integer corners)
+            X, Y = ex[k] + f * (ex[(k + 1) % 4] - ex[k]), ey[k] + f * (ey[(k + 1) % 4] - ey[k])
+        elif mode == 3:
+            k = rng.integers(4); X, Y = rng.uniform(-9, 9), ey[k]    # level with a vertex
+        else:
+            k = rng.integers(4); X, Y = ex[k], rng.uniform(-9, 9)
+        got = L.ora_gridcell(dptr(ex), dptr(ey), float(X), float(Y))
+        want = NL.gridcell(list(ex), list(ey), float(X), float(Y))
+        assert bool(got) == want, (list(ex), list(ey), X, Y)
+        n_on += mode in (1, 2)
+    assert n_on > 1000
+
+
+def test_inpoly_bit_equal_incl_ray_through_vertices():
+    rng = np.random.default_rng(5)
+    for it in range(4000):
+        n = int(rng.integers(3, 12))
+        ang = np.sort(rng.uniform(0, 2 * np.pi, n))
+        r = rng.uniform(1.0, 6.0, n)
+        px, py = r * np.cos(ang), r * np.sin(ang)
+        if it % 2 == 0:
+            px, py = np.round(px), np.round(py)                      # integer vertices: rays through vertices, collinear runs
+        px, py = np.append(px, px[0]), np.append(py, py[0])          # closed
+        mode = it % 4
+        if mode == 0:
+            x, y = rng.uniform(-7, 7, 2)
+        elif mode == 1:
+            k = rng.integers(n); x, y = px[k] - abs(rng.normal()) - 0.5, py[k]     # vertex on the ray
+        elif mode == 2:
+            k = rng.integers(n); x, y = px[k], py[k]                               # on a vertex
+        else:
+            k = rng.integers(n); x, y = 0.5 * (px[k] + px[k + 1]), 0.5 * (py[k] + py[k + 1])
+        for onin in (0, 1):
+            got = L.ora_inpoly(float(x), float(y), n + 1, dptr(arr(px)), dptr(arr(py)), onin)
+            want = NL.inpoly(float(x), float(y), list(zip(px.tolist(), py.tolist())), onin=bool(onin))
+            assert bool(got) == want, (it, onin, x, y, px.tolist(), py.tolist())
+
+
+# ---------------------------------------------------------------- intersect_reflect
+def test_intersect_reflect_bit_equal_on_the_synthetic_coastline():
+    """Random and axis-parallel moves near every kind of boundary segment of the synthetic world
+    (vertical, horizontal, diagonal; land and open), with and without a skipped segment."""
+    from common import SMALL, World, make_params
+    from oracle.oracle import Oracle
+    w = World(**SMALL)
+    b = w.bounds()
+    o = Oracle().create(make_params(w, 8))
+    o.set_grid(w.grid()); o.set_bounds(b)
+    bx, by = np.asarray(b["bnd_x"], float).reshape(-1, 2), np.asarray(b["bnd_y"], float).reshape(-1, 2)
+    segs = [(bx[i, 0], by[i, 0], bx[i, 1], by[i, 1]) for i in range(len(bx))]
+    land = [bool(v) for v in b["land"]]
+    rng = np.random.default_rng(11)
+    f = [C.c_double() for _ in range(4)]
+    hits = 0
+    for it in range(3000):
+        i = int(rng.integers(len(segs)))
+        mx, my = 0.5 * (segs[i][0] + segs[i][2]), 0.5 * (segs[i][1] + segs[i][3])
+        d = rng.uniform(20.0, 1500.0)
+        a = rng.uniform(0, 2 * np.pi)
+        X0, Y0 = mx + d * np.cos(a), my + d * np.sin(a)
+        X1, Y1 = mx - d * np.cos(a) * rng.uniform(0.1, 1.5), my - d * np.sin(a) * rng.uniform(0.1, 1.5)
+        if it % 5 == 1:
+            X1 = X0                                                   # vertical move
+        if it % 5 == 2:
+            Y1 = Y0                                                   # horizontal move
+        skip_in = int(rng.integers(0, len(segs) + 1)) if it % 3 == 0 else 0
+        skip, water = C.c_int32(skip_in), C.c_int32(0)
+        got = L.ora_intersect_reflect(o.ctx, float(X0), float(Y0), float(X1), float(Y1), *[C.byref(v) for v in f], C.byref(skip), C.byref(water))
+        want = NL.intersect_reflect(segs, land, float(X0), float(Y0), float(X1), float(Y1), skip_in)
+        assert got == want[0] and skip.value == want[5] and bool(water.value) == want[6], (it, got, want)
+        if got:
+            hits += 1
+            for k in range(4):
+                assert same(f[k].value, want[1 + k]), (it, k, f[k].value, want)
+    assert hits > 1000
+    o.destroy()

@@ -127,26 +127,25 @@ def test_vturb_long_horizon_distribution():
     assert ss.ks_2samp(fg["z"], fo["z"]).pvalue > 0.2
     assert abs(np.mean(fg["z"]) - np.mean(fo["z"])) <= 1e-3 * H
     assert np.array_equal(st[0][:3], st[1][:3]) or np.abs(st[0][:3] - st[1][:3]).max() <= 2
-    # fall-back rates: the oracle sweeps all 4 ws - 1 intervals of the VTurb spline, the device only
-    # the 32-knot window around the particle, so it takes the branch less often
-    assert 0.3 <= sg.sum() / max(1, so.sum()) <= 1.3, (int(sg.sum()), int(so.sum()))
+    # fall-back rates: both sides examine every interval of the VTurb fit
+    assert 0.6 <= sg.sum() / max(1, so.sum()) <= 1.5, (int(sg.sum()), int(so.sum()))
 
 
-def test_vturb_full_sigs_option_matches_reference_rate():
-    """ltgpu_params.vturb_full_sigs = 1: the VTurb fit is swept over all 4 ws - 1 intervals for
-    SigErr like the reference (ver_turb:278-279), so the fall-back RATE equals the oracle's; with
-    the default (window only) the device takes the branch less often."""
+def test_vturb_sigerr_rate_matches_reference_and_window_option():
+    """Default: SIGS examines every interval of the 4 ws-knot VTurb fit like the reference
+    (ver_turb:278-279), so the fall-back RATE equals the oracle's.  ltgpu_params.vturb_window_sigs = 1
+    (opt-in approximation) examines only the 32 knots around the particle and takes the branch less often."""
     n = 6000
     out = {}
-    for full in (0, 1):
-        rg, ro, res, ev, st, fg, fo, sg, so = _pair(n, 1, sigerr=True, world_kw={}, **dict(PASSIVE, HTurbOn=1, VTurbOn=1, vturb_full_sigs=full))
+    for window in (0, 1):
+        rg, ro, res, ev, st, fg, fo, sg, so = _pair(n, 1, sigerr=True, world_kw={}, **dict(PASSIVE, HTurbOn=1, VTurbOn=1, vturb_window_sigs=window))
         dz = np.abs(fg["z"] - fo["z"]) / 30.0
         clean = (sg == 0) & (so == 0)
         assert dz[clean].max() <= 1e-9 and clean.mean() > 0.95
-        out[full] = (int(sg.sum()), int(so.sum()))
+        out[window] = (int(sg.sum()), int(so.sum()))
     assert out[0][1] == out[1][1]                               # the oracle ignores the switch
-    assert 0.7 <= out[1][0] / out[1][1] <= 1.4, out             # ~110 events: +-10 % is one sigma
-    assert out[0][0] < out[1][0], out
+    assert 0.7 <= out[0][0] / out[0][1] <= 1.4, out             # ~110 events: +-10 % is one sigma
+    assert out[1][0] < out[0][0], out
 
 
 @pytest.mark.parametrize("name", ["passive", "hturb_salttemp", "oyster4_settle", "tidal7"])
@@ -445,3 +444,40 @@ def test_unlocated_particle_does_not_fault():
     f = g.fetch(("x", "status"))
     assert np.all(f["status"][:4] == -1) and np.isfinite(f["x"]).all()
     g.destroy()
+
+
+def _vturb_run(monkeypatch, n, env, world_kw=SMALL, nint=4, **kw):
+    for k in ("LTGPU_VTURB_LEGACY", "LTGPU_VTURB_CHUNK"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    w = World(**world_kw)
+    prm = make_params(w, n, **dict(PASSIVE, HTurbOn=1, VTurbOn=1, **kw))
+    g = LtransLib()
+    setup(g, w, prm, n)
+    run(g, w, 1, nint=nint)
+    f, s = g.fetch(), g.fetch_sigerr()
+    g.destroy()
+    return f, s
+
+
+def test_vturb_fit_walk_kernels_vs_round1_fused_kernel(monkeypatch):
+    """k_vbuild (one warp per column) + k_vwalk against the round-1 per-thread kernel on the same
+    particles: the same fit up to the rounding of the moving average (direct 8-term sums, like the
+    reference, instead of a running sum), the same walk."""
+    for wk, H in ((SMALL, 30.0), (GULF, 600.0)):
+        fa, sa = _vturb_run(monkeypatch, 1500, {}, world_kw=wk)
+        fb, sb = _vturb_run(monkeypatch, 1500, {"LTGPU_VTURB_LEGACY": "1"}, world_kw=wk)
+        clean = (sa == 0) & (sb == 0)
+        dz = np.abs(fa["z"] - fb["z"]) / H
+        assert clean.mean() > 0.98 and dz[clean].max() <= 1e-10, (float(clean.mean()), float(dz[clean].max()))
+        assert np.abs(fa["x"] - fb["x"])[clean].max() <= 1e-9 * 1e5 and np.array_equal(fa["status"], fb["status"])
+
+
+def test_vturb_chunked_scratch_is_invisible(monkeypatch):
+    """the fit -> walk scratch is sized for a chunk of particles; many small chunks = one big one, bit for bit"""
+    fa, sa = _vturb_run(monkeypatch, 1500, {})
+    fb, sb = _vturb_run(monkeypatch, 1500, {"LTGPU_VTURB_CHUNK": "96"})
+    for k in ("x", "y", "z", "status", "r_ele"):
+        assert np.array_equal(fa[k], fb[k]), k
+    assert np.array_equal(sa, sb)

@@ -7,7 +7,7 @@ from common import World, LtransLib, make_params, setup, run
 from oracle.oracle import Oracle
 w = World(); n = 20000
 for name, kw in (("advection only", dict(HTurbOn=0, VTurbOn=0)), ("HTurb only", dict(HTurbOn=1, VTurbOn=0)), ("HTurb + VTurb", dict(HTurbOn=1, VTurbOn=1)),
-                 ("HTurb + VTurb, vturb_full_sigs", dict(HTurbOn=1, VTurbOn=1, vturb_full_sigs=1))):
+                 ("HTurb + VTurb, window-only SIGS (opt-in)", dict(HTurbOn=1, VTurbOn=1, vturb_window_sigs=1))):
     prm = make_params(w, n, Behavior=0, settlementon=0, mortality=0, **kw)
     g, o = LtransLib(), Oracle()
     setup(g, w, prm, n); setup(o, w, prm, n); o.set_threads(os.cpu_count() or 1)

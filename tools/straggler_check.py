@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from common import World, LtransLib, make_params
 n = 1_000_000; rank = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-w = World(); prm = make_params(w, n, Behavior=0, settlementon=0, mortality=0, TrackCollisions=0, vturb_full_sigs=int(os.environ.get('FULL_SIGS', '0')))
+w = World(); prm = make_params(w, n, Behavior=0, settlementon=0, mortality=0, TrackCollisions=0, vturb_window_sigs=int(os.environ.get('WINDOW_SIGS', '0')))
 g = LtransLib().create(prm); g.set_grid(w.grid()); g.set_bounds(w.bounds())
 x, y, z, dob, r, u, v = w.seed_particles(n, seed=1234 + rank); g.set_particles(x, y, z, dob, None, r, u, v, first_id=1 + rank * n)
 recs = [w.record(k) for k in range(12)]
