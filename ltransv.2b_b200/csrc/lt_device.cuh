@@ -571,7 +571,7 @@ LT_DEV bool sigs_classify_s(double S, double S1, double S2, double& sigma, doubl
         if (D1D2 == 0.0) return true;
         // T = MAX(D1/D2, D2/D1) is the quotient with the larger magnitude on top; it can only
         // exceed 2 when that magnitude exceeds twice the other, so most intervals skip the division
-        const double a = fabs(D1), b = fabs(D2), hi = fmax(a, b), lo = fmin(a, b);
+        const double a = fabs(D1), b = fabs(D2), hi = a > b ? a : b, lo = a > b ? b : a;
         if (!(hi > 2.0 * lo)) return true;
         T = qdiv(hi, lo);
         if (T <= 2.0) return true;
@@ -652,24 +652,24 @@ LT_DEVN double hpval_interval(double T, double X1, double X2, double Y1, double 
     return S + (TM * ((E2 - E1) * (D1 + D2) + TM * (D1 - D2)) + SIG * ((E1 * EMS - E2) * D1 + (E1 - E2 * EMS) * D2)) * qrcp(E);
 }
 
-// YPC1 interior / end formulas (tension_module.f90:852-978)
-LT_DEV double ypc1_end(double SI, double T) { return SI >= 0.0 ? fmin(fmax(0.0, T), 3.0 * SI) : fmax(fmin(0.0, T), 3.0 * SI); }
+// YPC1 interior / end formulas (tension_module.f90:852-978).  MIN(MAX(0,T), M) / MAX(MIN(0,T), -M) are
+// clamps of T to [0, M] / [-M, 0] (M >= 0), written as two compares: FP64 fmin / fmax cost several
+// instructions each and these clamps were 14 % of k_advect (profiles/r02_notes.md).
+LT_DEV double clampd(double t, double lo, double hi) { return t < lo ? lo : (t > hi ? hi : t); }
+LT_DEV double ypc1_end(double SI, double T) { const double m = 3.0 * SI; return SI >= 0.0 ? clampd(T, 0.0, m) : clampd(T, m, 0.0); }
+LT_DEV double ypc1_clamp(double T, double SIM1, double SI)
+{
+    const double ASIM1 = fabs(SIM1), ASI = fabs(SI), m = 3.0 * (ASIM1 < ASI ? ASIM1 : ASI);
+    const bool pos = !signbit(ASIM1 > ASI ? SIM1 : SI);               // SGN = SIGN(1, SI), or of SIM1 when it is the larger
+    return clampd(T, pos ? 0.0 : -m, pos ? m : 0.0);
+}
 LT_DEV double ypc1_mid(double DXIM1, double DXI, double SIM1, double SI)
 {
-    double T = qdiv(DXIM1 * SI + DXI * SIM1, DXIM1 + DXI);
-    double ASIM1 = fabs(SIM1), ASI = fabs(SI);
-    double SGN = copysign(1.0, SI);
-    if (ASIM1 > ASI) SGN = copysign(1.0, SIM1);
-    return SGN > 0.0 ? fmin(fmax(0.0, T), 3.0 * fmin(ASIM1, ASI)) : fmax(fmin(0.0, T), -3.0 * fmin(ASIM1, ASI));
+    return ypc1_clamp(qdiv(DXIM1 * SI + DXI * SIM1, DXIM1 + DXI), SIM1, SI);
 }
-
 LT_DEV double ypc1_mid_r(double DXIM1, double DXI, double SIM1, double SI, double rsum)
 {   // ypc1_mid with 1/(DXIM1+DXI) supplied
-    double T = (DXIM1 * SI + DXI * SIM1) * rsum;
-    double ASIM1 = fabs(SIM1), ASI = fabs(SI);
-    double SGN = copysign(1.0, SI);
-    if (ASIM1 > ASI) SGN = copysign(1.0, SIM1);
-    return SGN > 0.0 ? fmin(fmax(0.0, T), 3.0 * fmin(ASIM1, ASI)) : fmax(fmin(0.0, T), -3.0 * fmin(ASIM1, ASI));
+    return ypc1_clamp((DXIM1 * SI + DXI * SIM1) * rsum, SIM1, SI);
 }
 
 // TSPSI(N=4) + HVAL, or the linint fallback: the water-column profile value of

@@ -115,7 +115,7 @@ LT_DEV bool sigerr_candidate(double s, double ypa, double ypb, double& T)
 {   // interval with chord slope s and end slopes ypa, ypb: convexity case with T in the band?
     const double D1 = s - ypa, D2 = ypb - s;
     if (!(D1 * D2 > 0.0)) return false;
-    const double a = fabs(D1), b = fabs(D2), hi = fmax(a, b), lo = fmin(a, b);
+    const double a = fabs(D1), b = fabs(D2), hi = a > b ? a : b, lo = a > b ? b : a;
     if (!(hi > LT_BAND_LO * lo && hi < LT_BAND_HI * lo)) return false;
     T = fmax(qdiv(D1, D2), qdiv(D2, D1));
     return T > 2.0;

@@ -481,3 +481,93 @@ def test_vturb_chunked_scratch_is_invisible(monkeypatch):
     for k in ("x", "y", "z", "status", "r_ele"):
         assert np.array_equal(fa[k], fb[k]), k
     assert np.array_equal(sa, sb)
+
+
+def _first_divergence(w, prm, n, nexternal, habitat=None, tol=1e-9):
+    """CUDA and oracle side by side for nexternal external steps, compared after EVERY internal step.
+    Returns (first step with a deviation > tol per particle or -1, whether the two SigErr fall-back
+    counters had moved differently by then, fall-back totals, final fetches)."""
+    from oracle.oracle import Oracle
+    g, o = LtransLib(), Oracle()
+    setup(g, w, prm, n, habitat=habitat); setup(o, w, prm, n, habitat=habitat); o.set_threads(os.cpu_count() or 1)
+    L = float(max(np.ptp(w.x_r), np.ptp(w.y_r))); H = float(w.h.max())
+    first = np.full(n, -1); explained = np.zeros(n, bool); moved_diff = np.zeros(n, bool)
+    sg0 = np.zeros(n, np.int32); so0 = np.zeros(n, np.int32)
+    stepIT = prm.dt // prm.idt
+    k = 0
+    for p in range(1, nexternal + 1):
+        if p > 2:
+            rec = w.record(p)
+            g.push_hydro(rec); g.rotate_hydro(); o.push_hydro(rec); o.rotate_hydro()
+        for it in range(1, stepIT + 1):
+            k += 1
+            g.step(p, it); o.step(p, it)
+            fg, fo = g.fetch(("x", "y", "z", "status", "r_ele")), o.fetch(("x", "y", "z", "status", "r_ele"))
+            sg, so = g.fetch_sigerr(), o.fetch_sigerr()
+            moved_diff |= (sg - sg0) != (so - so0)
+            fb_now = ((sg - sg0) > 0) | ((so - so0) > 0)              # a fall-back on either side in THIS step
+            sg0, so0 = sg, so
+            d = np.maximum(np.maximum(np.abs(fg["x"] - fo["x"]), np.abs(fg["y"] - fo["y"])) / L, np.abs(fg["z"] - fo["z"]) / H)
+            new = (first < 0) & (d > tol)
+            first[new] = k
+            explained[new] = moved_diff[new] | fb_now[new]
+            same_so_far = ~moved_diff
+            assert np.array_equal(fg["status"][same_so_far], fo["status"][same_so_far]), k
+            assert np.array_equal(fg["r_ele"][same_so_far & (first < 0)], fo["r_ele"][same_so_far & (first < 0)]), k
+    out = (first, explained, moved_diff, int(sg0.sum()), int(so0.sum()), g.fetch(), o.fetch(), (g.drain_events(1 << 16), o.drain_events(1 << 16)))
+    g.destroy(); o.destroy()
+    return out
+
+
+def test_config1_first_divergence_over_all_1440_steps():
+    """BASELINE configs[0] in full (130x130x20, 5,000 passive particles, RK4 only, 2 days = 1,440 internal
+    steps), CUDA vs oracle after EVERY step.  North-star gate: trajectories within 1e-9 with identical cell
+    ids and events.  The one branch on which two correct implementations part is the reference's SigErr
+    fall-back, so the claim checked is: a particle's FIRST deviation above 1e-9 appears
+    either in a step in which one of the two sides took a fall-back (both may, on different splines of that
+    step: seen 7 times in 7.2e6 particle-steps, each with a deviation of exactly 0 the step before), or after
+    the two fall-back counters have moved differently; everything else agrees to 1e-9 for the whole run."""
+    w = World(); n = 5000
+    prm = make_params(w, n, **PASSIVE)
+    first, explained, moved_diff, ng, no, fg, fo, ev = _first_divergence(w, prm, n, 48)
+    deviated = first >= 0
+    unexplained = int((deviated & ~explained).sum())
+    print("config 1, 1440 steps: never deviated %.3f, fall-back histories identical %.3f, fall-backs %d (CUDA) / %d (oracle), "
+          "unexplained first deviations %d" % (1 - deviated.mean(), 1 - moved_diff.mean(), ng, no, unexplained))
+    assert unexplained == 0, unexplained
+    same = ~moved_diff                                            # identical fall-back history => 1e-9 for the whole run
+    L = float(max(np.ptp(w.x_r), np.ptp(w.y_r))); H = float(w.h.max())
+    d = np.maximum(np.maximum(np.abs(fg["x"] - fo["x"]), np.abs(fg["y"] - fo["y"])) / L, np.abs(fg["z"] - fo["z"]) / H)
+    assert d[same & ~deviated].max() <= 1e-9
+    assert np.array_equal(fg["status"], fo["status"]) and ev[0] == ev[1]
+    assert 0.7 <= ng / no <= 1.4, (ng, no)
+
+
+CHES = dict(ni=120, nj=80, us=20, dlon=0.02, dlat=0.018)
+GULF_MID = dict(ni=256, nj=192, us=36, hmin=50.0, hmax=3000.0, dlon=0.08, dlat=0.072, speed=0.9)
+
+
+@pytest.mark.parametrize("name", ["config3_oysters", "config4_gulf"])
+def test_configs_3_and_4_worlds_turbulence_off_first_divergence(name):
+    """The worlds and switches of BASELINE configs[2] (Chesapeake-scale grid, Behavior 4, settlement polygons
+    with holes, mortality) and configs[3] (Gulf-scale levels and depths, buoyant Behavior 6, open boundary)
+    with turbulence off, 2,000 particles, 3 external steps, compared after every internal step."""
+    if name == "config3_oysters":
+        w = World(**CHES)
+        prm = make_params(w, 2000, HTurbOn=0, VTurbOn=0, Behavior=4, settlementon=1, holesExist=1, mortality=1, ErrorFlag=3,
+                          pediage=3600.0, deadage=2.5 * 3600.0)
+        hab = w.habitat(npoly=64)
+    else:
+        w = World(**GULF_MID)
+        prm = make_params(w, 2000, HTurbOn=0, VTurbOn=0, Behavior=6, sink=0.002, settlementon=0, mortality=0, ErrorFlag=3, OpenOceanBoundary=1)
+        hab = None
+    first, explained, moved_diff, ng, no, fg, fo, ev = _first_divergence(w, prm, 2000, 3, habitat=hab)
+    deviated = first >= 0
+    assert int((deviated & ~explained).sum()) == 0
+    assert (1 - deviated.mean()) > 0.9
+    same = ~moved_diff
+    for k in ("status", "endpoly", "hitBottom", "hitLand"):
+        assert np.array_equal(fg[k][same], fo[k][same]), k
+    assert np.array_equal(fg["lifespan"][same], fo["lifespan"][same])
+    if name == "config3_oysters":
+        assert (fg["status"] == -2).sum() > 0 and (fg["status"] == -1).sum() > 0        # some settled, some died
