@@ -447,6 +447,31 @@ def main():
             del E2
             torch.cuda.empty_cache()
 
+    # ---- secondary entry: the opt-in single-precision random walk on the headline configuration --------
+    if not args.no_secondary and not args.particles:
+        cf = dict(cfg); cf["prm"] = dict(cfg["prm"], vturb_fp32_walk=1)
+        E3 = Engine(cf, n, rank, local, keys)
+        E3.step(); E3.step(); E3.g.sync()
+        if world_size > 1:
+            dist.barrier()
+        ms3 = 0.0
+        for _ in range(2):
+            E3.g.timer_start(); E3.step(); ms3 += E3.g.timer_stop()
+        E3.g.kernel_times(True); E3.step(); km3, ks3 = E3.g.kernel_times(False)
+        t3 = torch.tensor([ms3], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ms3 = float(t3.item())
+        kk = [v / max(1, ks3) for v in km3[:3]]
+        c3 = config_dict(cf, n, world_size, E3.prm); c3["vturb_fp32_walk"] = 1
+        c3["workload"] += "; OPT-IN single-precision random walk (statistical parity only, not the headline)"
+        secondary.append({"config": c3, "steps": 2, "warmup": 2, "dtype": "f64 fit + f32 walk",
+                          "value": n * world_size * E3.stepIT * 2 / (ms3 * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms3 / 2,
+                          "kernels_ms": {"k_advect": kk[0], "k_vturb": kk[1], "k_finish": kk[2]}})
+        E3.g.destroy()
+        del E3
+        torch.cuda.empty_cache()
+
     if rank == 0:
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None,

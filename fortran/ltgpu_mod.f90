@@ -40,7 +40,7 @@ MODULE LTGPU_MOD
     INTEGER(C_INT)  :: holesExist, seed
     REAL(C_DOUBLE)  :: PI
     INTEGER(C_INT)  :: ErrorFlag, SaltTempOn, TrackCollisions, FreeSlip
-    INTEGER(C_INT)  :: rng_mode, field_dtype, vturb_window_sigs, reserved1
+    INTEGER(C_INT)  :: rng_mode, field_dtype, vturb_window_sigs, vturb_fp32_walk
   END TYPE ltgpu_params
 
   TYPE, BIND(C) :: ltgpu_event
@@ -286,7 +286,7 @@ CONTAINS
     prm%rng_mode = LTGPU_RNG_PHILOX      ! counter-based stream keyed on particle id and step
     prm%field_dtype = LTGPU_F32          ! ROMS history files are single precision: lossless
     prm%vturb_window_sigs = 0            ! reference semantics of the VTurb SigErr fall-back
-    prm%reserved1 = 0
+    prm%vturb_fp32_walk = 0              ! the random walk in FP64 like the reference
   END SUBROUTINE ltgpu_fill_params
 
   ! STOP with the library's message on any status other than OK (there is no CPU fallback)

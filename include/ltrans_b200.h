@@ -110,7 +110,10 @@ typedef struct ltgpu_params {
                                 * linint (ver_turb:278-279, 300-336).  1 (opt-in approximation): only the
                                 * 32 knots around the particle are examined, so the fall-back fires
                                 * ~30 % less often than the reference's */
-    int32_t reserved1;
+    int32_t vturb_fp32_walk;   /* 0 (default): the random-displacement walk in FP64 like the reference.
+                                * 1 (opt-in): HVAL / HPVAL / Box-Muller of the 60 sub-steps in FP32; the
+                                * spline fit, the Philox stream and the position stay FP64.  Statistical
+                                * parity only (BASELINE north star, turbulent runs); never the headline */
 } ltgpu_params;
 
 /* one buffered per-particle event (drained in ascending particle id) */

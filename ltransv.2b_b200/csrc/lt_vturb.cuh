@@ -504,3 +504,111 @@ LT_DEV void vwalk_particle(const LtDev& D, int n, int base)
     if (sigerr) D.nsig[n] += 1;
     D.s_turbv[n] = P_zc - ParZc;                                        // :342
 }
+
+// ------------------------------------------------- opt-in single-precision walk ----
+// ltgpu_params.vturb_fp32_walk = 1 (default 0).  BASELINE.json's north star accepts statistical parity
+// for turbulent runs ("the dispersion statistics are compared within a stated tolerance"): this walk
+// evaluates HVAL / HPVAL and the Box-Muller deviates of the 60 sub-steps in FP32 (knot values, slopes,
+// tension factors and the Philox words are the FP64 path's; the position itself stays FP64 and enters
+// the spline as a single-precision offset from the interval's left knot).  It is NOT the headline:
+// bench.py reports it as a secondary entry, gated by tests/test_parity_gpu.py::test_fp32_walk_*.
+struct IvF {
+    double X1d, X2d;                    // interval ends, FP64 (containment test, offset origin)
+    float DX, rDX, Y1, S1, S, D1, D2, SIG, EMS, rE, rSE;
+    int I, reg;
+};
+LT_DEV void ivf_setup(IvF& c, double Y1, double Y2, double P1, double P2_, double sigma)
+{
+    const double DX = c.X2d - c.X1d, S = (Y2 - Y1) / DX;
+    c.DX = (float)DX; c.rDX = 1.0f / c.DX; c.Y1 = (float)Y1; c.S1 = (float)P1; c.S = (float)S;
+    c.D1 = (float)(S - P1); c.D2 = (float)(P2_ - S);                  // differences formed in FP64: no cancellation in FP32
+    c.SIG = fabsf((float)sigma);
+    c.reg = c.SIG < 1.e-4f ? 0 : 2;                                    // below 1e-4 the exponential form cancels in FP32: cubic
+    if (c.reg == 2) {
+        const double sg = fabs(sigma), EMS = exp(-sg), TM = 1.0 - EMS, E = TM * (sg * (1.0 + EMS) - TM - TM);
+        c.EMS = (float)EMS; c.rE = (float)(1.0 / E); c.rSE = (float)(1.0 / (sg * E));   // once per interval, in FP64
+    }
+}
+LT_DEV float hpval_f(const IvF& c, float U)
+{   // U = T - X1
+    const float B2 = U * c.rDX, B1 = 1.0f - B2, D1 = c.D1, D2 = c.D2;
+    if (c.reg == 0) return c.S1 + B2 * (D1 + D2 - 3.0f * B1 * (D2 - D1));
+    const float SIG = c.SIG, SB1 = SIG * B1, SB2 = SIG - SB1;
+    if (-SB1 > 85.0f || -SB2 > 85.0f) return c.S;
+    const float EMS = c.EMS, TM = 1.0f - EMS, E1 = __expf(-SB1), E2 = __expf(-SB2);
+    return c.S + (TM * ((E2 - E1) * (D1 + D2) + TM * (D1 - D2)) + SIG * ((E1 * EMS - E2) * D1 + (E1 - E2 * EMS) * D2)) * c.rE;
+}
+LT_DEV float hval_f(const IvF& c, float U)
+{
+    const float B2 = U * c.rDX, B1 = 1.0f - B2, D1 = c.D1, D2 = c.D2;
+    if (c.reg == 0) return c.Y1 + U * (c.S1 + B2 * (D1 + B1 * (D1 - D2)));
+    const float SIG = c.SIG, SB1 = SIG * B1, SB2 = SIG - SB1;
+    if (-SB1 > 85.0f || -SB2 > 85.0f) return c.Y1 + c.S * U;
+    const float EMS = c.EMS, TM = 1.0f - EMS, TS = TM * TM, TP = 1.0f + EMS, E1 = __expf(-SB1), E2 = __expf(-SB2);
+    return c.Y1 + c.S * U + c.DX * (TM * (TP - E1 - E2) * (D1 + D2) +
+           SIG * ((E2 + EMS * (E1 - 2.0f) - B1 * TS) * D1 + (E1 + EMS * (E2 - 2.0f) - B2 * TS) * D2)) * c.rSE;
+}
+
+template <class T, int PH>
+LT_DEV void vwalk_particle_f32(const LtDev& D, int n, int base)
+{
+    if (!D.s_act[n]) return;
+    const int i = n - base;
+    const float background = 1.0E-6f;                                   // ledger 2
+    const double P_zc = D.s_pzc[n], P_depth = D.s_depth[n], P_zetac = D.s_zec[n];
+    const int p2 = 4 * D.P.ws;
+    VbKnots K; K.p2 = p2; K.Z1 = D.vz1[i]; K.ZN = D.vzn[i]; K.H = (K.ZN - K.Z1) * (1.0 / (double)p2);
+    const double rH = qrcp(K.H);
+    const int kw = D.vka[i];
+    int ka = kw & 0xffff, ia = ka, ib = min(ka + VW - 2, p2 - 1);
+    bool sigerr = (kw >> 16) != 0;
+    const double* W = D.vw + i;
+    const size_t ld = D.vw_stride;
+    const Rng g = make_rng(D, n);
+    const float deltat = 2.0f, twopi = (float)(2.0 * D.P.PI);
+    const int loop = D.P.idt / 2;
+    double ParZc = P_zc;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    IvF c; c.I = -1; c.X1d = 0.0; c.X2d = 0.0; c.reg = 0;
+    auto load_iv = [&](double zq) {
+        if (c.I >= 0 && zq >= c.X1d && zq < c.X2d) return;
+        int I;
+        if (zq < K.Z1) { I = 1; c.X1d = K.x(1); c.X2d = K.x(2); }
+        else if (zq > K.ZN) { I = p2 - 1; c.X1d = K.x(I); c.X2d = K.x(I + 1); }
+        else {
+            I = (int)floor((zq - K.Z1) * rH + 0.5); I = max(1, min(p2 - 1, I));
+            c.X1d = K.x(I); c.X2d = K.x(I + 1);
+            while (I > 1 && zq < c.X1d) { --I; c.X2d = c.X1d; c.X1d = K.x(I); }
+            while (I < p2 - 1 && !(zq < c.X2d)) { ++I; c.X1d = c.X2d; c.X2d = K.x(I + 1); }
+        }
+        if (I < ia || I > ib) vwalk_refit<T, PH>(D, n, i, I, ka, ia, ib, sigerr);
+        const int q = I - ka;
+        c.I = I;
+        ivf_setup(c, W[(size_t)q * ld], W[(size_t)(q + 1) * ld], W[(size_t)(VW + q) * ld], W[(size_t)(VW + q + 1) * ld], W[(size_t)(2 * VW + q) * ld]);
+    };
+#pragma unroll 1
+    for (int it = 0; it < loop; ++it) {
+        float Kprimec = 0.0f;
+        if (!(ParZc < P_depth || ParZc > P_zetac)) {
+            load_iv(ParZc);
+            Kprimec = sigerr ? c.S : hpval_f(c, (float)(ParZc - c.X1d));
+        }
+        const float KprimeZc = -1.0f * Kprimec * deltat;
+        const double Z3rdc = ParZc + (double)(0.5f * KprimeZc);
+        float KH3rdc;
+        if (Z3rdc < P_depth || Z3rdc > P_zetac) KH3rdc = background;
+        else {
+            load_iv(Z3rdc);
+            const float U = (float)(Z3rdc - c.X1d);
+            KH3rdc = sigerr ? c.Y1 + c.S * U : hval_f(c, U);
+            if (KH3rdc < background) KH3rdc = background;
+        }
+        if ((it & 1) == 0) rnd = philox(g, 1u + (unsigned)(it >> 1));
+        const unsigned w1 = (it & 1) ? rnd.z : rnd.x, w2 = (it & 1) ? rnd.w : rnd.y;
+        const float u1 = ((float)(w1 >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(w2 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float DEV = sqrtf(-2.0f * __logf(u1)) * __cosf(twopi * u2);
+        ParZc = ParZc + (double)(KprimeZc + DEV * sqrtf(2.0f * KH3rdc * deltat));
+    }
+    if (sigerr) D.nsig[n] += 1;
+    D.s_turbv[n] = P_zc - ParZc;
+}

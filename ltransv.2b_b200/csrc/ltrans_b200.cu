@@ -92,6 +92,12 @@ __global__ void __launch_bounds__(LT_BLK_VW, LT_MIN_VW) k_vwalk(const __grid_con
     if (n < base + count) vwalk_particle<T, PH>(D, n, base);
 }
 template <class T, int PH>
+__global__ void __launch_bounds__(LT_BLK_VW, LT_MIN_VW) k_vwalk_f32(const __grid_constant__ LtDev D, int base, int count)
+{
+    const int n = base + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < base + count) vwalk_particle_f32<T, PH>(D, n, base);
+}
+template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_FIN, LT_MIN_FIN) k_finish(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -612,7 +618,8 @@ static int32_t launch_step(ltgpu_ctx* ctx)
         for (int base = 0; base < D.n; base += ctx->vt_chunk) {
             const int count = std::min(ctx->vt_chunk, D.n - base);
             k_vbuild<T, PH><<<(count + LT_BLK_VB - 1) / LT_BLK_VB, LT_BLK_VB, smem, st>>>(D, base, count);
-            k_vwalk<T, PH><<<(count + LT_BLK_VW - 1) / LT_BLK_VW, LT_BLK_VW, 0, st>>>(D, base, count);
+            if (ctx->prm.vturb_fp32_walk) k_vwalk_f32<T, PH><<<(count + LT_BLK_VW - 1) / LT_BLK_VW, LT_BLK_VW, 0, st>>>(D, base, count);
+            else k_vwalk<T, PH><<<(count + LT_BLK_VW - 1) / LT_BLK_VW, LT_BLK_VW, 0, st>>>(D, base, count);
             ctx->launches += 2;
         }
     }

@@ -43,7 +43,7 @@ class Params(C.Structure):
         ("holesExist", C.c_int32), ("seed", C.c_int32), ("PI", C.c_double),
         ("ErrorFlag", C.c_int32), ("SaltTempOn", C.c_int32), ("TrackCollisions", C.c_int32),
         ("FreeSlip", C.c_int32), ("rng_mode", C.c_int32), ("field_dtype", C.c_int32),
-        ("vturb_window_sigs", C.c_int32), ("reserved1", C.c_int32),
+        ("vturb_window_sigs", C.c_int32), ("vturb_fp32_walk", C.c_int32),
     ]
 
     @classmethod

@@ -76,7 +76,7 @@ def params_from_namelist(nml, **over):
     p = Params.shipped()
     names = {f[0].lower(): f[0] for f in Params._fields_}
     for k, v in flat.items():
-        if k in names and names[k] not in ("rng_mode", "field_dtype", "vturb_window_sigs", "reserved1"):
+        if k in names and names[k] not in ("rng_mode", "field_dtype", "vturb_window_sigs", "vturb_fp32_walk"):
             if isinstance(v, bool):
                 v = int(v)
             setattr(p, names[k], v)

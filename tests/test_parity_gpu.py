@@ -571,3 +571,35 @@ def test_configs_3_and_4_worlds_turbulence_off_first_divergence(name):
     assert np.array_equal(fg["lifespan"][same], fo["lifespan"][same])
     if name == "config3_oysters":
         assert (fg["status"] == -2).sum() > 0 and (fg["status"] == -1).sum() > 0        # some settled, some died
+
+
+def test_fp32_walk_option_statistical_parity(monkeypatch):
+    """ltgpu_params.vturb_fp32_walk = 1 (opt-in, never the headline): the 60 random-displacement sub-steps
+    in single precision.  North star, turbulent runs: dispersion statistics within a stated tolerance.
+    Same Philox stream as the FP64 walk, so the two are compared particle by particle AND in distribution:
+      * median |dz| / H <= 1e-5, 99 % of the particles within 1e-2 of the depth (differences amplify where K is
+        small and K' large), identical cells and status for >= 99.5 %;
+      * depth distributions: two-sample KS p > 0.2, means within 1e-3 H, standard deviations within 1 %;
+      * the well-mixed condition: particles released uniformly over the column stay uniformly distributed
+        (chi-square over 10 depth classes of the relative depth, FP32 against FP64)."""
+    from scipy import stats as ss
+    n = 20000
+    f64, s64 = _vturb_run(monkeypatch, n, {}, world_kw={}, nint=30)
+    f32, s32 = _vturb_run(monkeypatch, n, {}, world_kw={}, nint=30, vturb_fp32_walk=1)
+    H = 30.0
+    dz = np.abs(f32["z"] - f64["z"]) / H
+    assert np.median(dz) <= 1e-5 and np.quantile(dz, 0.99) <= 1e-2, (float(np.median(dz)), float(np.quantile(dz, 0.99)))
+    assert np.mean(f32["r_ele"] == f64["r_ele"]) >= 0.995 and np.mean(f32["status"] == f64["status"]) >= 0.999
+    assert ss.ks_2samp(f32["z"], f64["z"]).pvalue > 0.2
+    assert abs(f32["z"].mean() - f64["z"].mean()) <= 1e-3 * H
+    assert abs(f32["z"].std() / f64["z"].std() - 1.0) <= 0.01
+    w = World()
+    x, y, z0, dob, r, u, v = w.seed_particles(n)
+    i0 = np.clip(np.searchsorted(w.x_r[0], x) - 1, 0, w.ni - 1); j0 = np.clip(np.searchsorted(w.y_r[:, 0], y) - 1, 0, w.nj - 1)
+    h = w.h[j0, i0]
+    act = f64["status"] == 0
+    rel32, rel64 = -f32["z"][act] / h[act], -f64["z"][act] / h[act]
+    c32, _ = np.histogram(rel32, bins=10, range=(0, 1)); c64, _ = np.histogram(rel64, bins=10, range=(0, 1))
+    chi2 = float(np.sum((c32 - c64) ** 2 / np.maximum(c32 + c64, 1)))
+    assert chi2 < 27.9, chi2                                       # chi-square, 10 d.o.f. (two-sample form), p = 0.002
+    assert abs(int(s32.sum()) - int(s64.sum())) <= 0.05 * s64.sum() + 5      # same fit, same SigErr verdicts
