@@ -323,34 +323,10 @@ class World:
         polys = np.array(rows, dtype=np.float64)
         hol = np.array(hrows, dtype=np.float64).reshape(-1, 6)
 
-        def specs(tab, idlist):
-            start, size, maxdis = [], [], []
-            for q in idlist:
-                r = np.nonzero(tab[:, 0] == q)[0]
-                start.append(r[0] + 1); size.append(len(r))
-                maxdis.append(np.sqrt((tab[r, 3] - tab[r, 1]) ** 2 + (tab[r, 4] - tab[r, 2]) ** 2).max())
-            return (np.array(start, dtype=np.int32), np.array(size, dtype=np.int32),
-                    np.array(maxdis, dtype=np.float64))
-        ps, pz, pm = specs(polys, ids)
-        hs, hz, hm = specs(hol, hids) if len(hids) else (np.zeros(0, np.int32),) * 2 + (np.zeros(0),)
-        # polygons per rho element: bounding circle vs element bounding box (conservative)
-        ex = g["rx"][g["RE"] - 1]; ey = g["ry"][g["RE"] - 1]
-        xmin, xmax, ymin, ymax = ex.min(1), ex.max(1), ey.min(1), ey.max(1)
-        ptr, idx = [0], []
-        cxs = np.array([polys[s - 1, 1] for s in ps]); cys = np.array([polys[s - 1, 2] for s in ps])
-        hit = ((cxs[None] + pm[None] >= xmin[:, None]) & (cxs[None] - pm[None] <= xmax[:, None])
-               & (cys[None] + pm[None] >= ymin[:, None]) & (cys[None] - pm[None] <= ymax[:, None]))
-        for e in range(len(ex)):
-            idx += list(np.nonzero(hit[e])[0]); ptr.append(len(idx))
-        hptr, hidx = [0], []
-        for q in ids:
-            hidx += [n for n, hq in enumerate(hids) if hol[hs[n] - 1, 5] == q]; hptr.append(len(hidx))
-        return dict(pedges=len(polys), polys=np.ascontiguousarray(polys.T),     # Fortran (pedges,5)
-                    hedges=len(hol), holes=np.ascontiguousarray(hol.T) if len(hol) else np.zeros((6, 0)),
-                    poly_id=np.array(ids, dtype=np.int32), poly_start=ps, poly_size=pz, poly_maxdis=pm,
-                    hole_id=np.array(hids, dtype=np.int32), hole_start=hs, hole_size=hz, hole_maxdis=hm,
-                    elepoly_ptr=np.array(ptr, dtype=np.int32), elepoly_idx=np.array(idx, dtype=np.int32),
-                    polyhole_ptr=np.array(hptr, dtype=np.int32), polyhole_idx=np.array(hidx, dtype=np.int32))
+        # polyspecs / holespecs / elepolys / polyholes exactly as createPolySpecs builds them
+        # (settlement_module.f90:245-480), through the bucketed routine of host/polyspecs.py
+        from .polyspecs import create_poly_specs
+        return create_poly_specs(g["rx"][g["RE"] - 1], g["ry"][g["RE"] - 1], polys, hol)
 
     # ------------------------------------------------------------- particles --
     def _interior_water(self, margin):

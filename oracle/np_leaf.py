@@ -579,3 +579,35 @@ def slevel(zeta, depth, sc, cs, hc32, vtransform):
     if vtransform == 3:
         return zeta * (1.0 + sc) + hc32 * sc + (h - hc32) * cs
     raise ValueError("Illegal Vtransform number")
+
+
+# ---------------------------------------------------------------- settlement_module.f90 (set-up)
+def create_poly_specs_literal(r_ele_x, r_ele_y, polys, maxbdis):
+    """createPolySpecs' element loop as written (settlement_module.f90:296-402): every element against every
+    row of `polys` ([id, cx, cy, ex, ey] per row), with the `polytail%num` skip, the edge-point test, and the
+    corner test on the polygon's last row.  maxbdis: {id: radius}.  -> list of polygon ids per element."""
+    pedges = len(polys)
+    first, count = {}, {}
+    for i, row in enumerate(polys):
+        q = int(round(row[0]))
+        first.setdefault(q, i)
+        count[q] = count.get(q, 0) + 1
+    out = []
+    for e in range(len(r_ele_x)):
+        ex, ey = list(r_ele_x[e]), list(r_ele_y[e])
+        lst = []
+        for j in range(pedges):
+            q = int(round(polys[j][0]))
+            if lst and lst[-1] == q:
+                continue
+            if gridcell(ex, ey, polys[j][3], polys[j][4]):
+                lst.append(q)
+                continue
+            if j == pedges - 1 or polys[j][0] != polys[j + 1][0]:
+                near = any(math.sqrt((ex[k] - polys[j][1]) ** 2 + (ey[k] - polys[j][2]) ** 2) < maxbdis[q] for k in range(4))
+                if near:
+                    pts = [(polys[first[q] + k][3], polys[first[q] + k][4]) for k in range(count[q])]
+                    if any(inpoly(ex[k], ey[k], pts) for k in range(4)):
+                        lst.append(q)
+        out.append(lst)
+    return out
