@@ -174,93 +174,154 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
             K.Z1 = lag(D.LW4, z1[0], z1[1], z1[2]);
             K.ZN = lag(D.LW4, zc[L - 1], zc[2 * L - 1], zc[3 * L - 1]);
             K.H = (K.ZN - K.Z1) * rp2;
-            // ---- 2. per level: segment slope / intercept (ver_turb:126-133) and the first sample at or
-            //         above the level.  The samples newx(j) = z1 + (j - 4) hs are an arithmetic progression,
-            //         so that index is a quotient, checked against the sample's own formula.
-            for (int l = lane; l < L - 1; l += 32) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const double zlo = zc[t * L + l], zhi = zc[t * L + l + 1], klo = kc[t * L + l], khi = kc[t * L + l + 1];
-                    const double s = qdiv(klo - khi, zlo - zhi);
-                    sl[t * L + l] = s; ic[t * L + l] = klo - s * zlo;
-                    if (t == 1 || !shared_geom) {
-                        int g = P2 + 4;
-                        if (hs[t] > 0.0) {
-                            g = 4 + (int)ceil((zlo - z1[t]) * qrcp(hs[t]));
-                            g = max(5, min(P2 + 4, g));
-                            while (g <= P2 + 3 && fma((double)(g - 4), hs[t], z1[t]) < zlo) ++g;
-                            while (g > 5 && !(fma((double)(g - 5), hs[t], z1[t]) < zlo)) --g;
-                        }
-                        cm[t * L + l] = g;                                     // level 0 is never looked up
-                    }
+            // ---- 2-4, common case: ONE profile instead of three.  Without the clamps of ver_turb:264-268 the
+            //         chain resample -> 8-point mean -> time polynomial -> (b + 4c + f)/6 is linear in the KH
+            //         values, and with the levels at the same relative depths at the three hydro times
+            //         (shared_geom) the resampling weights do not depend on the time either, so
+            //         ifity(k) = [resample + mean] of K4(level) = sum_t LW4(t) KH_t(level), on the geometry of
+            //         the centre time.  The clamps cannot bind when the time-interpolated KH of EVERY level is
+            //         >= 0 at the three internal times (every knot value is an average of convex combinations
+            //         of those): checked per column; otherwise the three-profile path below runs.  The two
+            //         agree to rounding (sums of the same terms in another order).
+            bool single = shared_geom && k1[0] >= 0.0;
+            for (int l0 = 0; l0 < L; l0 += 32) {
+                const int l = l0 + lane;
+                bool ok = true;
+                if (l < L) {
+                    const double a = kc[l], b = kc[L + l], c = kc[2 * L + l], db = a - b, df = c - b;
+                    ok = b + (w0b * db + w2b * df) >= 0.0 && b + (w0c * db + w2c * df) >= 0.0 && b + (w0f * db + w2f * df) >= 0.0;
+                    sl[L + l] = lag(D.LW4, a, b, c);                           // K4(level), parked in the slope table's second row
                 }
+                single = __all_sync(VT_FULL, ok) && single;
             }
             __syncwarp();
-            // ---- 3. resample (ver_turb:135-177): sample j lies in the segment above the highest interior
-            //         level at or below it = the reference's walking `jlo`.  Each lane takes RS consecutive
-            //         samples: one bisection over the level marks, then a cursor.
-            {
-                const int ja = 5 + lane * RS, jb = min(ja + RS, P2 + 4);
-                if (shared_geom) {
+            if (single) {
+                const double* k4 = sl + L; const double* zt = zc + L;          // centre-time geometry
+                const double z1c = z1[1], hsc = hs[1];
+                for (int l = lane; l < L - 1; l += 32) {
+                    const double zlo = zt[l], zhi = zt[l + 1], klo = k4[l], khi = k4[l + 1];
+                    const double sseg = qdiv(klo - khi, zlo - zhi);
+                    sl[l] = sseg; ic[l] = klo - sseg * zlo;
+                    int g = P2 + 4;
+                    if (hsc > 0.0) {
+                        g = 4 + (int)ceil((zlo - z1c) * qrcp(hsc));
+                        g = max(5, min(P2 + 4, g));
+                        while (g <= P2 + 3 && fma((double)(g - 4), hsc, z1c) < zlo) ++g;
+                        while (g > 5 && !(fma((double)(g - 5), hsc, z1c) < zlo)) --g;
+                    }
+                    cm[l] = g;
+                }
+                const double k4top = k4[L - 1], k4bot = k4[0];
+                __syncwarp();
+                {
+                    const int ja = 5 + lane * RS, jb = min(ja + RS, P2 + 4);
                     if (ja < jb) {
-                        const int* c = cm + L;
-                        int lo = 0, hi = L - 2;                                // segment = #{m in 1 .. L-2 : c[m] <= j}
-                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (c[mid] <= ja) lo = mid; else hi = mid - 1; }
-                        int nxt = lo < L - 2 ? c[lo + 1] : 0x7fffffff;
-                        double s0_ = sl[lo], b0_ = ic[lo], s1_ = sl[L + lo], b1_ = ic[L + lo], s2_ = sl[2 * L + lo], b2_ = ic[2 * L + lo];
+                        int lo = 0, hi = L - 2;
+                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cm[mid] <= ja) lo = mid; else hi = mid - 1; }
+                        int nxt = lo < L - 2 ? cm[lo + 1] : 0x7fffffff;
+                        double sseg = sl[lo], bseg = ic[lo];
                         for (int j = ja; j < jb; ++j) {
-                            while (nxt <= j) {
-                                ++lo; nxt = lo < L - 2 ? c[lo + 1] : 0x7fffffff;
-                                s0_ = sl[lo]; b0_ = ic[lo]; s1_ = sl[L + lo]; b1_ = ic[L + lo]; s2_ = sl[2 * L + lo]; b2_ = ic[2 * L + lo];
-                            }
-                            const double dj = (double)(j - 4);
-                            ys[j] = fma(s0_, fma(dj, hs[0], z1[0]), b0_);
-                            ys[NSP + j] = fma(s1_, fma(dj, hs[1], z1[1]), b1_);
-                            ys[2 * NSP + j] = fma(s2_, fma(dj, hs[2], z1[2]), b2_);
+                            while (nxt <= j) { ++lo; nxt = lo < L - 2 ? cm[lo + 1] : 0x7fffffff; sseg = sl[lo]; bseg = ic[lo]; }
+                            ys[j] = fma(sseg, fma((double)(j - 4), hsc, z1c), bseg);
                         }
                     }
-                } else {
-#pragma unroll
+                    if (lane < 4) { ys[1 + lane] = k1[0]; ys[P2 + 4 + lane] = k4top; }      // pads: KHb(1) below, the top value above
+                }
+                __syncwarp();
+                for (int k = 1 + lane; k <= P2; k += 32) {
+                    const double* y = ys + min(k, P2 - 1);
+                    const double avg = (y[0] + y[1] + y[2] + y[3] + y[4] + y[5] + y[6] + y[7]) * 0.125;
+                    fy[k] = k == 1 ? k4bot : (k == P2 ? k4top : avg);
+                }
+            } else {
+                // ---- 2. per level: segment slope / intercept (ver_turb:126-133) and the first sample at or
+                //         above the level.  The samples newx(j) = z1 + (j - 4) hs are an arithmetic progression,
+                //         so that index is a quotient, checked against the sample's own formula.
+                for (int l = lane; l < L - 1; l += 32) {
+    #pragma unroll
                     for (int t = 0; t < 3; ++t) {
+                        const double zlo = zc[t * L + l], zhi = zc[t * L + l + 1], klo = kc[t * L + l], khi = kc[t * L + l + 1];
+                        const double s = qdiv(klo - khi, zlo - zhi);
+                        sl[t * L + l] = s; ic[t * L + l] = klo - s * zlo;
+                        if (t == 1 || !shared_geom) {
+                            int g = P2 + 4;
+                            if (hs[t] > 0.0) {
+                                g = 4 + (int)ceil((zlo - z1[t]) * qrcp(hs[t]));
+                                g = max(5, min(P2 + 4, g));
+                                while (g <= P2 + 3 && fma((double)(g - 4), hs[t], z1[t]) < zlo) ++g;
+                                while (g > 5 && !(fma((double)(g - 5), hs[t], z1[t]) < zlo)) --g;
+                            }
+                            cm[t * L + l] = g;                                     // level 0 is never looked up
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- 3. resample (ver_turb:135-177): sample j lies in the segment above the highest interior
+                //         level at or below it = the reference's walking `jlo`.  Each lane takes RS consecutive
+                //         samples: one bisection over the level marks, then a cursor.
+                {
+                    const int ja = 5 + lane * RS, jb = min(ja + RS, P2 + 4);
+                    if (shared_geom) {
                         if (ja < jb) {
-                            const int* c = cm + t * L;
-                            int lo = 0, hi = L - 2;
+                            const int* c = cm + L;
+                            int lo = 0, hi = L - 2;                                // segment = #{m in 1 .. L-2 : c[m] <= j}
                             while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (c[mid] <= ja) lo = mid; else hi = mid - 1; }
                             int nxt = lo < L - 2 ? c[lo + 1] : 0x7fffffff;
-                            double s = sl[t * L + lo], b = ic[t * L + lo];
+                            double s0_ = sl[lo], b0_ = ic[lo], s1_ = sl[L + lo], b1_ = ic[L + lo], s2_ = sl[2 * L + lo], b2_ = ic[2 * L + lo];
                             for (int j = ja; j < jb; ++j) {
-                                while (nxt <= j) { ++lo; nxt = lo < L - 2 ? c[lo + 1] : 0x7fffffff; s = sl[t * L + lo]; b = ic[t * L + lo]; }
-                                ys[t * NSP + j] = fma(s, fma((double)(j - 4), hs[t], z1[t]), b);
+                                while (nxt <= j) {
+                                    ++lo; nxt = lo < L - 2 ? c[lo + 1] : 0x7fffffff;
+                                    s0_ = sl[lo]; b0_ = ic[lo]; s1_ = sl[L + lo]; b1_ = ic[L + lo]; s2_ = sl[2 * L + lo]; b2_ = ic[2 * L + lo];
+                                }
+                                const double dj = (double)(j - 4);
+                                ys[j] = fma(s0_, fma(dj, hs[0], z1[0]), b0_);
+                                ys[NSP + j] = fma(s1_, fma(dj, hs[1], z1[1]), b1_);
+                                ys[2 * NSP + j] = fma(s2_, fma(dj, hs[2], z1[2]), b2_);
+                            }
+                        }
+                    } else {
+    #pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            if (ja < jb) {
+                                const int* c = cm + t * L;
+                                int lo = 0, hi = L - 2;
+                                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (c[mid] <= ja) lo = mid; else hi = mid - 1; }
+                                int nxt = lo < L - 2 ? c[lo + 1] : 0x7fffffff;
+                                double s = sl[t * L + lo], b = ic[t * L + lo];
+                                for (int j = ja; j < jb; ++j) {
+                                    while (nxt <= j) { ++lo; nxt = lo < L - 2 ? c[lo + 1] : 0x7fffffff; s = sl[t * L + lo]; b = ic[t * L + lo]; }
+                                    ys[t * NSP + j] = fma(s, fma((double)(j - 4), hs[t], z1[t]), b);
+                                }
                             }
                         }
                     }
+                    if (lane < 12) {                                               // the pads, ver_turb:169-177
+                        const int t = lane >> 2, r = lane & 3;
+                        ys[t * NSP + 1 + r] = k1[0];                               // ledger 11: KHb(1) for all three times
+                        ys[t * NSP + P2 + 4 + r] = t == 0 ? kN[0] : t == 1 ? kN[1] : kN[2];
+                    }
                 }
-                if (lane < 12) {                                               // the pads, ver_turb:169-177
-                    const int t = lane >> 2, r = lane & 3;
-                    ys[t * NSP + 1 + r] = k1[0];                               // ledger 11: KHb(1) for all three times
-                    ys[t * NSP + P2 + 4 + r] = t == 0 ? kN[0] : t == 1 ? kN[1] : kN[2];
+                __syncwarp();
+                // ---- 4. 8-point moving average, time polynomial, clamp, (b + 4c + f)/6 (ver_turb:184-275)
+                //         fy overlays the column, which step 3 was the last to read
+                for (int k = 1 + lane; k <= P2; k += 32) {
+                    double my[3];
+    #pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const double* y = ys + t * NSP + min(k, P2 - 1);
+                        const double avg = (y[0] + y[1] + y[2] + y[3] + y[4] + y[5] + y[6] + y[7]) * 0.125;
+                        my[t] = k == 1 ? k1[t] : (k == P2 ? kN[t] : avg);          // ends: the data values (ver_turb:197-210)
+                    }
+                    const double db = my[0] - my[1], df = my[2] - my[1];       // lag(): centre + weighted differences
+                    double fb = my[1] + (w0b * db + w2b * df), fc = my[1] + (w0c * db + w2c * df), ff = my[1] + (w0f * db + w2f * df);
+                    fb = fb < 0.0 ? 0.0 : fb; fc = fc < 0.0 ? 0.0 : fc; ff = ff < 0.0 ? 0.0 : ff;
+                    {   // (ifityb + 4 ifityc + ifityf)/6: quotient by the constant from its reciprocal + one correction (<= 1 ulp)
+                        const double a6 = fb + 4.0 * fc + ff, q6 = a6 * 0.16666666666666666;
+                        fy[k] = fma(fma(-6.0, q6, a6), 0.16666666666666666, q6);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
-            // ---- 4. 8-point moving average, time polynomial, clamp, (b + 4c + f)/6 (ver_turb:184-275)
-            //         fy overlays the column, which step 3 was the last to read
-            for (int k = 1 + lane; k <= P2; k += 32) {
-                double my[3];
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const double* y = ys + t * NSP + min(k, P2 - 1);
-                    const double avg = (y[0] + y[1] + y[2] + y[3] + y[4] + y[5] + y[6] + y[7]) * 0.125;
-                    my[t] = k == 1 ? k1[t] : (k == P2 ? kN[t] : avg);          // ends: the data values (ver_turb:197-210)
-                }
-                const double db = my[0] - my[1], df = my[2] - my[1];       // lag(): centre + weighted differences
-                double fb = my[1] + (w0b * db + w2b * df), fc = my[1] + (w0c * db + w2c * df), ff = my[1] + (w0f * db + w2f * df);
-                fb = fb < 0.0 ? 0.0 : fb; fc = fc < 0.0 ? 0.0 : fc; ff = ff < 0.0 ? 0.0 : ff;
-                {   // (ifityb + 4 ifityc + ifityf)/6: quotient by the constant from its reciprocal + one correction (<= 1 ulp)
-                    const double a6 = fb + 4.0 * fc + ff, q6 = a6 * 0.16666666666666666;
-                    fy[k] = fma(fma(-6.0, q6, a6), 0.16666666666666666, q6);
-                }
-            }
-            __syncwarp();
             // ---- 5. chord slope of every interval, then the YPC1 knot slopes (tension:852-978).  Interior
             //         intervals have length H: their chord slope is a product and the three-point formula
             //         (DXIM1 SI + DXI SIM1)/(DXIM1 + DXI) the mean of the two chord slopes.

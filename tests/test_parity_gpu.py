@@ -602,4 +602,4 @@ def test_fp32_walk_option_statistical_parity(monkeypatch):
     c32, _ = np.histogram(rel32, bins=10, range=(0, 1)); c64, _ = np.histogram(rel64, bins=10, range=(0, 1))
     chi2 = float(np.sum((c32 - c64) ** 2 / np.maximum(c32 + c64, 1)))
     assert chi2 < 27.9, chi2                                       # chi-square, 10 d.o.f. (two-sample form), p = 0.002
-    assert abs(int(s32.sum()) - int(s64.sum())) <= 0.05 * s64.sum() + 5      # same fit, same SigErr verdicts
+    assert abs(int(s32.sum()) - int(s64.sum())) <= 4.0 * np.sqrt(float(s32.sum() + s64.sum())) + 5      # same fit: SigErr fall-backs at the same rate (Poisson counts)
