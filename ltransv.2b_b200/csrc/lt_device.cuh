@@ -93,11 +93,11 @@ template <int PH> LT_DEV void pick3(double a0, double a1, double a2, double a3, 
     else if (PH == 2) { b = a2; c = a3; f = a0; }
     else { b = a3; c = a0; f = a1; }
 }
-// How the hydro fields are read.  At Gulf scale (3.3 GB of fields) a field line is touched by one or two
-// particles per step and then never again, while the kernels' thread-local scratch is re-read within
-// microseconds: LT_FIELD_LD = __ldcs marks the field lines evict-first so that they do not push that
-// scratch out of L2 (profiles/r02_notes.md: k_advect moved 14 KB of DRAM per particle-step, nearly all of
-// it local memory).  When the whole field set fits L2 (Baymouth: 19 MB) the hint costs nothing.
+// How the 4-level field profiles of k_advect are read.  At Gulf scale (3.3 GB of fields) a field line is
+// touched by one or two particles per step and then never again, while the kernels' thread-local scratch
+// is re-read within microseconds: LT_FIELD_LD = __ldcs marks those lines evict-first so that they do not
+// push the scratch out of L2 (k_advect 31.3 -> 29.6 ms per step at 12.5 M particles; no effect when the
+// whole field set fits L2).  The single-level / whole-column reads (LoadBCF::get) stay __ldg.
 #ifndef LT_FIELD_LD
 #define LT_FIELD_LD __ldcs
 #endif
@@ -114,7 +114,7 @@ template <int PH> struct LoadBCF<float, PH> {
     }
     static LT_DEV void get(const float* base, size_t idx, double& b, double& c, double& f)
     {
-        float4 q = LT_FIELD_LD(reinterpret_cast<const float4*>(base) + idx);
+        float4 q = __ldg(reinterpret_cast<const float4*>(base) + idx);
         float fb, fc, ff;
         if (PH == 0) { fb = q.x; fc = q.y; ff = q.z; } else if (PH == 1) { fb = q.y; fc = q.z; ff = q.w; }
         else if (PH == 2) { fb = q.z; fc = q.w; ff = q.x; } else { fb = q.w; fc = q.x; ff = q.y; }
@@ -132,7 +132,7 @@ template <int PH> struct LoadBCF<double, PH> {
     static LT_DEV void get(const double* base, size_t idx, double& b, double& c, double& f)
     {
         const double2* p = reinterpret_cast<const double2*>(base) + 2 * idx;
-        double2 lo = LT_FIELD_LD(p), hi = LT_FIELD_LD(p + 1);
+        double2 lo = __ldg(p), hi = __ldg(p + 1);
         pick3<PH>(lo.x, lo.y, hi.x, hi.y, b, c, f);
     }
 };
@@ -360,7 +360,7 @@ LT_DEVN void gather_bcf(const LtDev& D, const T* fld, int L, int lev0, const Ste
 // use, so one memory latency is exposed per profile instead of one per level.
 template <class T, int PH>
 LT_DEVN void gather4_bcf(const LtDev& D, const T* fld, int L, int lev0, const Stencil& s, int grid, int4 und,
-                         double* __restrict__ vs, int ld)
+                         double* __restrict__ vb, double* __restrict__ vc, double* __restrict__ vf)
 {
     // all 16 vector loads are issued first and held RAW (float4: 64 registers for f32; the
     // converted doubles would need 96 and spill), then converted and combined level by level
@@ -379,9 +379,9 @@ LT_DEVN void gather4_bcf(const LtDev& D, const T* fld, int L, int lev0, const St
         LoadBCF<T, PH>::pick(r[i][0], b0, c0, f0); LoadBCF<T, PH>::pick(r[i][1], b1, c1, f1);
         LoadBCF<T, PH>::pick(r[i][2], b2, c2, f2); LoadBCF<T, PH>::pick(r[i][3], b3, c3, f3);
         LT_FREESLIP4(b0, b1, b2, b3, c0, c1, c2, c3, f0, f1, f2, f3);
-        vs[i * ld] = combine(w, b0, b1, b2, b3);                 // the calling thread's strip of shared memory
-        vs[(4 + i) * ld] = combine(w, c0, c1, c2, c3);
-        vs[(8 + i) * ld] = combine(w, f0, f1, f2, f3);
+        vb[i] = combine(w, b0, b1, b2, b3);
+        vc[i] = combine(w, c0, c1, c2, c3);
+        vf[i] = combine(w, f0, f1, f2, f3);
     }
 }
 

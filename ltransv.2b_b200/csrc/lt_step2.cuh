@@ -72,46 +72,34 @@ LT_DEV double lag(const double* w, double b, double c, double f) { return c + (w
 
 // 4-knot spline value (TSPSI + HVAL of WCTS_ITPI, hydro:2619-2644) with the knot
 // reciprocals shared between the fields interpolated on the same knots.
-//
-// Where the knots live.  The three knot lines of one WCTS_ITPI call (4 abscissae + 5 reciprocals per
-// hydro time) and the 12 gathered profile values are handed between out-of-line routines (gather,
-// spline), i.e. through addressable memory.  As thread-local memory that was 24 KB of local loads /
-// stores per particle-step, and at Gulf scale -- where 3.3 GB of fields stream through L2 -- it was
-// written back to and re-read from DRAM: k_advect moved 14 KB of DRAM per particle-step and ran at
-// 70 % of the HBM peak on its own scratch (profiles/r02_notes.md).  They now live in a per-thread
-// strip of SHARED memory (LT_WS_DOUBLES doubles per thread, [slot][thread] so that a warp's accesses
-// are conflict-free): no L2 / DRAM traffic at all.
-#define LT_WS_KNOTS 27                 // 3 hydro times x (x[4], r1, r2, r3, r12, r23)
-#define LT_WS_VALS 12                  // one field's 4-level profile at the three hydro times
-#define LT_WS_DOUBLES (LT_WS_KNOTS + LT_WS_VALS)
-extern __shared__ double lt_ws_smem[];
-struct Knots4 {                        // view of one knot line in the calling thread's strip
-    double* p; int ld;                 // element i at p[i * ld]
-    LT_DEV double x(int i) const { return p[i * ld]; }
-    LT_DEV double r1() const { return p[4 * ld]; }
-    LT_DEV double r2() const { return p[5 * ld]; }
-    LT_DEV double r3() const { return p[6 * ld]; }
-    LT_DEV double r12() const { return p[7 * ld]; }
-    LT_DEV double r23() const { return p[8 * ld]; }
-};
-LT_DEV Knots4 knots_of(int t) { Knots4 k; k.ld = blockDim.x; k.p = lt_ws_smem + (size_t)(9 * t) * blockDim.x + threadIdx.x; return k; }
-LT_DEV double* vals_ws() { return lt_ws_smem + (size_t)LT_WS_KNOTS * blockDim.x + threadIdx.x; }
-LT_DEV void knots_prepare(const Knots4& k)
+struct Knots4 { double x[4], r1, r2, r3, r12, r23; };
+LT_DEV void knots_prepare(Knots4& k)
 {
-    const double x0 = k.x(0), x1 = k.x(1), x2 = k.x(2), x3 = k.x(3);
-    const double d1 = x1 - x0, d2 = x2 - x1, d3 = x3 - x2;
-    k.p[4 * k.ld] = qrcp(d1); k.p[5 * k.ld] = qrcp(d2); k.p[6 * k.ld] = qrcp(d3); k.p[7 * k.ld] = qrcp(d1 + d2); k.p[8 * k.ld] = qrcp(d2 + d3);
+    double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
+    k.r1 = qrcp(d1); k.r2 = qrcp(d2); k.r3 = qrcp(d3); k.r12 = qrcp(d1 + d2); k.r23 = qrcp(d2 + d3);
 }
 // the interval of a 4-knot spline that contains T, with its end slopes (YPC1) -- everything
 // SIGS and HVAL need (tension:852-978, 1026-1041)
 struct Iv4 { double X1, X2, Y1, Y2, P1, P2; };
+LT_DEV void spline4_prepare(const Knots4& k, double y0, double y1, double y2, double y3, double T, Iv4& v)
+{
+    const double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
+    const double s1 = (y1 - y0) * k.r1, s2 = (y2 - y1) * k.r2, s3 = (y3 - y2) * k.r3;
+    const int I = (T < k.x[0]) ? 0 : (T > k.x[3]) ? 2 : (T < k.x[2] ? (T < k.x[1] ? 0 : 1) : 2);
+    // interior-knot slope needed by every case: knot 1 for I = 0,1; knot 2 for I = 2
+    const bool hi = I == 2;
+    const double mA = ypc1_mid_r(hi ? d2 : d1, hi ? d3 : d2, hi ? s2 : s1, hi ? s3 : s2, hi ? k.r23 : k.r12);
+    if (I == 0) { v.X1 = k.x[0]; v.X2 = k.x[1]; v.Y1 = y0; v.Y2 = y1; v.P1 = ypc1_end(s1, s1 + d1 * (s1 - s2) * k.r12); v.P2 = mA; }
+    else if (I == 1) { v.X1 = k.x[1]; v.X2 = k.x[2]; v.Y1 = y1; v.Y2 = y2; v.P1 = mA; v.P2 = ypc1_mid_r(d2, d3, s2, s3, k.r23); }
+    else { v.X1 = k.x[2]; v.X2 = k.x[3]; v.Y1 = y2; v.Y2 = y3; v.P1 = mA; v.P2 = ypc1_end(s3, s3 + d3 * (s3 - s2) * k.r23); }
+}
 LT_DEV double linint4(const Knots4& k, double y0, double y1, double y2, double y3, double T)
 {   // linint fallback when SigErr (interpolation_module.f90:25-59), n = 4
     const double Y[4] = {y0, y1, y2, y3};
     int jlo = 1, jhi = 4;
-    for (;;) { int q = (jhi + jlo) / 2; if (k.x(q - 1) > T) jhi = q; else jlo = q; if (jhi - jlo == 1) break; }
-    double m = (Y[jlo - 1] - Y[jhi - 1]) / (k.x(jlo - 1) - k.x(jhi - 1));
-    return m * T + (Y[jlo - 1] - m * k.x(jlo - 1));
+    for (;;) { int q = (jhi + jlo) / 2; if (k.x[q - 1] > T) jhi = q; else jlo = q; if (jhi - jlo == 1) break; }
+    double m = (Y[jlo - 1] - Y[jhi - 1]) / (k.x[jlo - 1] - k.x[jhi - 1]);
+    return m * T + (Y[jlo - 1] - m * k.x[jlo - 1]);
 }
 
 // The reference's SIGS sweeps ALL intervals of the profile and leaves at the first one whose
@@ -137,16 +125,15 @@ LT_DEV bool sigerr_candidate(double s, double ypa, double ypb, double& T)
 // WCTS_ITPI (hydro:2619-2644).  One Newton loop per lane runs the solve of the interval that
 // holds T and the verdict-only solves of the other intervals.  (Flattening the solves of all 9
 // splines of one find_currents was tried and lost: 9 x 7 doubles of state spill.)
-LT_DEVN double spline4_eval2(const Knots4 k, double y0, double y1, double y2, double y3, double T, int& nsig)
+LT_DEVN double spline4_eval2(const Knots4& k, double y0, double y1, double y2, double y3, double T, int& nsig)
 {
-    const double x0 = k.x(0), x1 = k.x(1), x2 = k.x(2), x3 = k.x(3), r12 = k.r12(), r23 = k.r23();
-    const double d1 = x1 - x0, d2 = x2 - x1, d3 = x3 - x2;
-    const double s1 = (y1 - y0) * k.r1(), s2 = (y2 - y1) * k.r2(), s3 = (y3 - y2) * k.r3();
-    const double p0 = ypc1_end(s1, s1 + d1 * (s1 - s2) * r12), p1 = ypc1_mid_r(d1, d2, s1, s2, r12);
-    const double p2 = ypc1_mid_r(d2, d3, s2, s3, r23), p3 = ypc1_end(s3, s3 + d3 * (s3 - s2) * r23);
-    const int I = (T < x0) ? 0 : (T > x3) ? 2 : (T < x2 ? (T < x1 ? 0 : 1) : 2);
+    const double d1 = k.x[1] - k.x[0], d2 = k.x[2] - k.x[1], d3 = k.x[3] - k.x[2];
+    const double s1 = (y1 - y0) * k.r1, s2 = (y2 - y1) * k.r2, s3 = (y3 - y2) * k.r3;
+    const double p0 = ypc1_end(s1, s1 + d1 * (s1 - s2) * k.r12), p1 = ypc1_mid_r(d1, d2, s1, s2, k.r12);
+    const double p2 = ypc1_mid_r(d2, d3, s2, s3, k.r23), p3 = ypc1_end(s3, s3 + d3 * (s3 - s2) * k.r23);
+    const int I = (T < k.x[0]) ? 0 : (T > k.x[3]) ? 2 : (T < k.x[2] ? (T < k.x[1] ? 0 : 1) : 2);
     Iv4 v;
-    v.X1 = I == 0 ? x0 : I == 1 ? x1 : x2; v.X2 = I == 0 ? x1 : I == 1 ? x2 : x3;
+    v.X1 = I == 0 ? k.x[0] : I == 1 ? k.x[1] : k.x[2]; v.X2 = I == 0 ? k.x[1] : I == 1 ? k.x[2] : k.x[3];
     v.Y1 = I == 0 ? y0 : I == 1 ? y1 : y2; v.Y2 = I == 0 ? y1 : I == 1 ? y2 : y3;
     v.P1 = I == 0 ? p0 : I == 1 ? p1 : p2; v.P2 = I == 0 ? p1 : I == 1 ? p2 : p3;
     int err = 0, np = 0;
@@ -190,23 +177,21 @@ template <class T, int PH, bool W, int NF>
 LT_WCTS_ATTR void wcts2(const LtDev& D, const T* const* fld, const Stencil* const* st, const int* grid, int4 und, int L,
                   const ColK& col, int deplvl, double P_zb, double P_zc, double P_zf, int v, double* out, int& nsig)
 {
-    const Knots4 kb = knots_of(0), kc = knots_of(1), kf = knots_of(2);
-    double* vs = vals_ws(); const int ld = blockDim.x;
+    double vb[NF][4], vc[NF][4], vf[NF][4];
+    Knots4 kb, kc, kf;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double zb, zc, zf; zlev3<W>(D, col, deplvl - 1 + i, zb, zc, zf);
-        kb.p[i * ld] = zb; kc.p[i * ld] = zc; kf.p[i * ld] = zf;
-    }
+    for (int f = 0; f < NF; ++f) gather4_bcf<T, PH>(D, fld[f], L, deplvl - 1, *st[f], grid[f], und, vb[f], vc[f], vf[f]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) zlev3<W>(D, col, deplvl - 1 + i, kb.x[i], kc.x[i], kf.x[i]);
     knots_prepare(kb); knots_prepare(kc);
     const bool first = D.p == 1;                     // (b,b,c): the forward profile is not used
     if (!first) knots_prepare(kf);
     const double* w = v < 3 ? D.LW[v] : D.LW4;
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        gather4_bcf<T, PH>(D, fld[f], L, deplvl - 1, *st[f], grid[f], und, vs, ld);     // b: vs[0..3], c: vs[4..7], f: vs[8..11] (x ld)
-        double pb = spline4_eval2(kb, vs[0], vs[ld], vs[2 * ld], vs[3 * ld], P_zb, nsig);
-        double pc = spline4_eval2(kc, vs[4 * ld], vs[5 * ld], vs[6 * ld], vs[7 * ld], P_zc, nsig);
-        double pf = first ? 0.0 : spline4_eval2(kf, vs[8 * ld], vs[9 * ld], vs[10 * ld], vs[11 * ld], P_zf, nsig);
+        double pb = spline4_eval2(kb, vb[f][0], vb[f][1], vb[f][2], vb[f][3], P_zb, nsig);
+        double pc = spline4_eval2(kc, vc[f][0], vc[f][1], vc[f][2], vc[f][3], P_zc, nsig);
+        double pf = first ? 0.0 : spline4_eval2(kf, vf[f][0], vf[f][1], vf[f][2], vf[f][3], P_zf, nsig);
         out[f] = lag(w, pb, pc, pf);
     }
 }

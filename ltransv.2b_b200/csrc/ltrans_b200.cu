@@ -606,9 +606,7 @@ static int32_t launch_step(ltgpu_ctx* ctx)
     cudaStream_t st = ctx->compute;
     const bool vt = ctx->prm.VTurbOn != 0;
     if (ctx->timing) cudaEventRecord(ctx->tev[0], st);
-    const size_t ws_adv = sizeof(double) * LT_WS_DOUBLES * LT_BLK_ADV, ws_fin = sizeof(double) * LT_WS_DOUBLES * LT_BLK_FIN;
-    CK(cudaFuncSetAttribute(k_advect<T, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_adv));
-    k_advect<T, PH><<<(D.n + LT_BLK_ADV - 1) / LT_BLK_ADV, LT_BLK_ADV, ws_adv, st>>>(D);
+    k_advect<T, PH><<<(D.n + LT_BLK_ADV - 1) / LT_BLK_ADV, LT_BLK_ADV, 0, st>>>(D);
     ctx->launches++;
     if (ctx->timing) cudaEventRecord(ctx->tev[1], st);
     if (vt && ctx->vt_legacy) {
@@ -626,7 +624,7 @@ static int32_t launch_step(ltgpu_ctx* ctx)
         }
     }
     if (ctx->timing) cudaEventRecord(ctx->tev[2], st);
-    k_finish<T, PH><<<(D.n + LT_BLK_FIN - 1) / LT_BLK_FIN, LT_BLK_FIN, ws_fin, st>>>(D);
+    k_finish<T, PH><<<(D.n + LT_BLK_FIN - 1) / LT_BLK_FIN, LT_BLK_FIN, 0, st>>>(D);
     ctx->launches++;
     if (ctx->timing) {
         cudaEventRecord(ctx->tev[3], st);
