@@ -155,12 +155,18 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
                 col.zb = o[4]; col.zc = o[5]; col.zf = o[6]; col.depth = o[7]; col.h = -1.0 * col.depth; P_zc = o[8];
             }
             // ---- 1. KH and depth of level l at the three hydro times (ver_turb:102-108) ----
+            //         plus, per level, what the single-profile test below needs: the time-interpolated KH at the
+            //         three internal times (>= 0 ?) and K4 = sum_t LW4(t) KH_t, parked in the slope table's second row
+            bool lev_ok = true;
             for (int l = lane; l < L; l += 32) {
                 double kb, kcc, kf, zb, zcc, zf;
                 gather_bcf_inl<T, PH>(D, fk, L, l, s0, G_RHO, s0.nd, kb, kcc, kf);
                 zlev3<true>(D, col, l, zb, zcc, zf);
                 kc[l] = kb; kc[L + l] = kcc; kc[2 * L + l] = kf;
                 zc[l] = zb; zc[L + l] = zcc; zc[2 * L + l] = zf;
+                const double db = kb - kcc, df = kf - kcc;
+                lev_ok = lev_ok && kcc + (w0b * db + w2b * df) >= 0.0 && kcc + (w0c * db + w2c * df) >= 0.0 && kcc + (w0f * db + w2f * df) >= 0.0;
+                sl[L + l] = lag(D.LW4, kb, kcc, kf);
             }
             __syncwarp();
             double z1[3], hs[3], k1[3], kN[3];
@@ -183,50 +189,36 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
             //         >= 0 at the three internal times (every knot value is an average of convex combinations
             //         of those): checked per column; otherwise the three-profile path below runs.  The two
             //         agree to rounding (sums of the same terms in another order).
-            bool single = shared_geom && k1[0] >= 0.0;
-            for (int l0 = 0; l0 < L; l0 += 32) {
-                const int l = l0 + lane;
-                bool ok = true;
-                if (l < L) {
-                    const double a = kc[l], b = kc[L + l], c = kc[2 * L + l], db = a - b, df = c - b;
-                    ok = b + (w0b * db + w2b * df) >= 0.0 && b + (w0c * db + w2c * df) >= 0.0 && b + (w0f * db + w2f * df) >= 0.0;
-                    sl[L + l] = lag(D.LW4, a, b, c);                           // K4(level), parked in the slope table's second row
-                }
-                single = __all_sync(VT_FULL, ok) && single;
-            }
-            __syncwarp();
+            const bool single = __all_sync(VT_FULL, lev_ok) && shared_geom && k1[0] >= 0.0;
             if (single) {
                 const double* k4 = sl + L; const double* zt = zc + L;          // centre-time geometry
-                const double z1c = z1[1], hsc = hs[1];
-                for (int l = lane; l < L - 1; l += 32) {
-                    const double zlo = zt[l], zhi = zt[l + 1], klo = k4[l], khi = k4[l + 1];
-                    const double sseg = qdiv(klo - khi, zlo - zhi);
-                    sl[l] = sseg; ic[l] = klo - sseg * zlo;
+                const double z1c = z1[1], hsc = hs[1], rhsc = qrcp(hsc);
+                // first sample at or above each level (the samples newx(j) = z1 + (j - 4) hs are an arithmetic
+                // progression: a quotient, checked against the sample's own formula); level 0 owns sample 5
+                for (int l = lane; l < L; l += 32) {
+                    const double zlo = zt[l];
                     int g = P2 + 4;
-                    if (hsc > 0.0) {
-                        g = 4 + (int)ceil((zlo - z1c) * qrcp(hsc));
+                    if (hsc > 0.0 && l < L - 1) {
+                        g = 4 + (int)ceil((zlo - z1c) * rhsc);
                         g = max(5, min(P2 + 4, g));
                         while (g <= P2 + 3 && fma((double)(g - 4), hsc, z1c) < zlo) ++g;
                         while (g > 5 && !(fma((double)(g - 5), hsc, z1c) < zlo)) --g;
                     }
-                    cm[l] = g;
+                    cm[l] = l == 0 ? 5 : g;
                 }
                 const double k4top = k4[L - 1], k4bot = k4[0];
                 __syncwarp();
-                {
-                    const int ja = 5 + lane * RS, jb = min(ja + RS, P2 + 4);
-                    if (ja < jb) {
-                        int lo = 0, hi = L - 2;
-                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cm[mid] <= ja) lo = mid; else hi = mid - 1; }
-                        int nxt = lo < L - 2 ? cm[lo + 1] : 0x7fffffff;
-                        double sseg = sl[lo], bseg = ic[lo];
-                        for (int j = ja; j < jb; ++j) {
-                            while (nxt <= j) { ++lo; nxt = lo < L - 2 ? cm[lo + 1] : 0x7fffffff; sseg = sl[lo]; bseg = ic[lo]; }
-                            ys[j] = fma(sseg, fma((double)(j - 4), hsc, z1c), bseg);
-                        }
-                    }
-                    if (lane < 4) { ys[1 + lane] = k1[0]; ys[P2 + 4 + lane] = k4top; }      // pads: KHb(1) below, the top value above
+                // one lane per segment [level l, level l + 1): slope / intercept (ver_turb:126-133) stay in
+                // registers, the segment's own samples cm[l] .. cm[l + 1] - 1 are evaluated in a row (the marks are
+                // monotone, so this is the reference's walking `jlo`, ver_turb:135-177)
+                for (int l = lane; l < L - 1; l += 32) {
+                    const double zlo = zt[l], klo = k4[l];
+                    const double sseg = qdiv(klo - k4[l + 1], zlo - zt[l + 1]), bseg = klo - sseg * zlo;
+                    const int ja = cm[l], jb = cm[l + 1];
+                    double dj = (double)(ja - 4);
+                    for (int j = ja; j < jb; ++j, dj += 1.0) ys[j] = fma(sseg, fma(dj, hsc, z1c), bseg);
                 }
+                if (lane < 4) { ys[1 + lane] = k1[0]; ys[P2 + 4 + lane] = k4top; }          // pads: KHb(1) below, the top value above
                 __syncwarp();
                 for (int k = 1 + lane; k <= P2; k += 32) {
                     const double* y = ys + min(k, P2 - 1);
@@ -333,20 +325,22 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
             }
             __syncwarp();
             for (int k = 3 + lane; k <= P2 - 2; k += 32) {
+                // the clamp interval is [0, m3] or [-m3, 0] by the sign of the chord slope of larger magnitude
+                // (tension:935-945), which on equal spacing is the sign of t itself (t = 0 when they cancel):
+                // clamp(t) = sign(t) min(|t|, m3), zeros included
                 const double s1 = sk[k - 1], s2 = sk[k], a1 = fabs(s1), a2 = fabs(s2), m3 = 3.0 * (a1 < a2 ? a1 : a2), t = 0.5 * (s1 + s2);
-                const bool pos = !signbit(a1 > a2 ? s1 : s2);                  // SIGN(1, SI), or of SIM1 when it is the larger
-                const double lo_ = pos ? 0.0 : -m3, hi_ = pos ? m3 : 0.0;
-                yp[k] = t < lo_ ? lo_ : (t > hi_ ? hi_ : t);
+                const double at = fabs(t);
+                yp[k] = copysign(at < m3 ? at : m3, t);
             }
             if (lane < 4) {                                                    // knots 1, 2, P2 - 1, P2: unequal spacing
                 const bool top = lane >= 2, end = lane == 0 || lane == 3;
                 const double sa = sk[top ? P2 - 2 : 1], sb = sk[top ? P2 - 1 : 2];         // left, right chord slope
                 const double da = top ? K.H : dE1, db_ = top ? dEN : K.H;
-                double v;
-                if (end) {   // YP(1) = clamp(SI + DXI (SI - S2)/(DXI + DX2)); YP(N) likewise from the other side
-                    const double si = top ? sb : sa, so = top ? sa : sb, di = top ? db_ : da;
-                    v = ypc1_end(si, si + qdiv(di * (si - so), da + db_));
-                } else v = ypc1_mid(da, db_, sa, sb);
+                // YP(1) = clamp(SI + DXI (SI - S2)/(DXI + DX2)), YP(N) likewise from the other side (tension:905-915,
+                // 962-972); knots 2 and P2 - 1 the three-point formula (:930-945): one quotient serves the four lanes
+                const double si = top ? sb : sa, so = top ? sa : sb, di = top ? db_ : da;
+                const double q = qdiv(end ? di * (si - so) : da * sb + db_ * sa, da + db_);
+                const double v = end ? ypc1_end(si, si + q) : ypc1_clamp(q, sa, sb);
                 yp[lane == 0 ? 1 : lane == 1 ? 2 : lane == 2 ? P2 - 1 : P2] = v;
             }
             __syncwarp();
