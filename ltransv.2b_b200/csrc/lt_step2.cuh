@@ -30,6 +30,20 @@
 #include "lt_device.cuh"
 
 struct ColK { double zb, zc, zf, depth, h; };
+// The s-level tables (SC | CS | SCW | CSW of getSlevel / getWlevel, hydro:2691-2777) in shared memory: every
+// kernel on the path starts with lev_tables_load().  As kernel parameters they sit in the constant bank,
+// where a lane-dependent index is served one distinct address at a time (5 % of k_vbuild's and 7 % of
+// k_advect's stall samples, profiles/r02_notes.md).
+__shared__ double s_levtab[4 * LT_MAXLEV];
+LT_DEV void lev_tables_load(const LtDev& D)
+{
+    const int ws = D.P.ws;                                              // us = ws - 1 entries of SC / CS are used
+    for (int i = threadIdx.x; i < 4 * ws; i += blockDim.x) {
+        const int t = i / ws, k = i - t * ws;
+        s_levtab[t * LT_MAXLEV + k] = t == 0 ? D.SC[k] : t == 1 ? D.CS[k] : t == 2 ? D.SCW[k] : D.CSW[k];
+    }
+    __syncthreads();
+}
 LT_DEV double zlev2(const LtDev& D, const ColK& c, double zeta, double sc, double cs)
 {
     double hc = (double)D.P.hc, S;
@@ -40,7 +54,7 @@ LT_DEV double zlev2(const LtDev& D, const ColK& c, double zeta, double sc, doubl
 template <bool W>
 LT_DEV void zlev3(const LtDev& D, const ColK& c, int k, double& zb, double& zc, double& zf)
 {   // level k (0-based) at the three hydro times; S and 1 + S/h are shared
-    double sc = W ? D.SCW[k] : D.SC[k], cs = W ? D.CSW[k] : D.CS[k];
+    const double sc = s_levtab[(W ? 2 * LT_MAXLEV : 0) + k], cs = s_levtab[(W ? 3 * LT_MAXLEV : LT_MAXLEV) + k];
     double hc = (double)D.P.hc;
     if (D.P.Vtransform == 1) {
         double S = hc * sc + (c.h - hc) * cs, q = 1.0 + qdiv(S, c.h);
@@ -481,12 +495,18 @@ LT_DEV bool advect_prologue(const LtDev& D, int n, AdvS& S)
     return true;
 }
 
+LT_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // one RK stage; stage times are (t-h, t, t, t+h) = versions 1,2,2,3 (ledger 6)
 template <class T, int PH>
 LT_DEV void advect_stage(const LtDev& D, AdvS& S, int stg)
 {
     const double eps6 = (double)kF32_1em6;
     double Uad, Vad, Wad;
+    // the u / v element records are on their way while the rho weights are worked out (-0.6 .. -3 %); asking for
+    // the field windows of the previous stage's levels the same way cost 13 % (they evict the thread-local
+    // lines the stage lives on) and a level search started from the previous stage's window changed nothing
+    prefetch_l1(S.st.u.q); prefetch_l1(S.st.v.q);
     stage_weights2(S.st, S.xs, S.ys);
     find_currents2<T, PH>(D, S.st, S.col, S.zs, S.P_zb, S.P_zc, S.P_zf, stg == 0 ? 1 : (stg == 3 ? 3 : 2), Uad, Vad, Wad, S.nsig);
     const double wgt = (stg == 0 || stg == 3) ? 1.0 : 2.0;

@@ -43,6 +43,7 @@ template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_ADV, LT_MIN_ADV) k_advect(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
+    lev_tables_load(D);
     AdvS S;
     bool act = n < D.n;
     if (act) act = advect_prologue<T, PH>(D, n, S);
@@ -59,6 +60,7 @@ template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_VT, LT_MIN_VT) k_vturb(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
+    lev_tables_load(D);
     if (n < D.n) vturb_particle<T, PH>(D, n);
 }
 // VTurb as fit + walk (lt_vturb.cuh): k_vbuild spreads the 32 lanes of a warp over ONE particle's water
@@ -82,6 +84,7 @@ template <class T, int PH, int MINB>
 __global__ void __launch_bounds__(LT_BLK_VB, MINB) k_vbuild(const __grid_constant__ LtDev D, int base, int count)
 {
     extern __shared__ double vb_smem[];
+    lev_tables_load(D);
     const int wib = threadIdx.x >> 5;
     const int warp_first = base + (blockIdx.x * (LT_BLK_VB / 32) + wib) * 32;
     if (warp_first >= base + count) return;
@@ -91,18 +94,21 @@ template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_VW, LT_MIN_VW) k_vwalk(const __grid_constant__ LtDev D, int base, int count)
 {
     const int n = base + blockIdx.x * blockDim.x + threadIdx.x;
+    lev_tables_load(D);                                                 // the refit of a walked-out window
     if (n < base + count) vwalk_particle<T, PH>(D, n, base);
 }
 template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_VW, LT_MIN_VW) k_vwalk_f32(const __grid_constant__ LtDev D, int base, int count)
 {
     const int n = base + blockIdx.x * blockDim.x + threadIdx.x;
+    lev_tables_load(D);
     if (n < base + count) vwalk_particle_f32<T, PH>(D, n, base);
 }
 template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_FIN, LT_MIN_FIN) k_finish(const __grid_constant__ LtDev D)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
+    lev_tables_load(D);
     if (n < D.n) finish_particle<T, PH>(D, n);
 }
 
@@ -341,7 +347,7 @@ struct ltgpu_ctx {
     int key_bits = 32;
     long long sorts = 0;
     // VTurb scratch (one chunk of particles between k_vbuild and k_vwalk)
-    int vt_chunk = 0; bool vt_legacy = false; int smem_per_sm = 228 * 1024;
+    int vt_chunk = 0; bool vt_legacy = false; int smem_per_sm = 228 * 1024; int vb_deep = -1;   // LTGPU_VB_DEEP: force the register variant
     // optional per-kernel timing (ltgpu_kernel_times)
     bool timing = false; cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; float tacc[4] = {0, 0, 0, 0}; long long tcount = 0;
 };
@@ -616,7 +622,7 @@ static int32_t launch_step(ltgpu_ctx* ctx)
         ctx->launches++;
     } else if (vt) {
         const size_t smem = sizeof(double) * (size_t)vb_smem_doubles(ctx->prm.ws) * (LT_BLK_VB / 32);
-        const bool deep = (smem + 1024) * LT_MIN_VB > (size_t)ctx->smem_per_sm;
+        const bool deep = ctx->vb_deep >= 0 ? ctx->vb_deep != 0 : (smem + sizeof(double) * 4 * LT_MAXLEV + 1024) * LT_MIN_VB > (size_t)ctx->smem_per_sm;
         auto kb = deep ? k_vbuild<T, PH, LT_MIN_VB - 1> : k_vbuild<T, PH, LT_MIN_VB>;
         CK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 // per device and function
         for (int base = 0; base < D.n; base += ctx->vt_chunk) {
@@ -698,6 +704,7 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     ctx->D.sb = 0; ctx->D.sc = 1; ctx->D.sf = 2; ctx->spare = 3;
     const char* so = getenv("LTGPU_SORT");
     ctx->sort_on = !(so && so[0] == '0');
+    { const char* vd = getenv("LTGPU_VB_DEEP"); if (vd) ctx->vb_deep = atoi(vd); }
     { const char* se = getenv("LTGPU_SORT_EVERY"); if (se && atoi(se) > 0) ctx->sort_every = atoi(se); }
     { const char* sm = getenv("LTGPU_SORT_MODE"); ctx->sort_mode = sm ? std::max(0, std::min(127, atoi(sm))) : 32; }
     { const char* vl = getenv("LTGPU_VTURB_LEGACY"); ctx->vt_legacy = vl && vl[0] == '1'; }     // round-1 fused k_vturb (A/B only)
