@@ -34,11 +34,11 @@ LT_DEV double shfl_d(double v, int src) { return __shfl_sync(VT_FULL, v, src); }
 //   B  [3 (4 ws + 8)] resampled KH of the three hydro times; later chord slopes and knot slopes
 //   M  [3 ws / 2 + 2] (3 ws ints) first sample at or above each level, per hydro time
 //   Q  [3 VT_QCAP + VT_QCAP / 2 + 8]  queue of pending solves (three operands + tag) + per-particle words
-//   O  [VT_SG][10 + 3]                the staged particles' own scalars (weights, zeta, depth; node ids)
+//   O  [VT_SG][20 + 3]                the staged particles' own scalars (weights, zeta, depth, knot line; node ids)
 //   S  [VT_SG][VT_STAGE_LD]           staged windows
 __host__ __device__ __forceinline__ int vb_smem_doubles(int ws)
 {
-    return 12 * ws + 3 * (4 * ws + 8) + (3 * ws / 2 + 2) + (3 * VT_QCAP + VT_QCAP / 2 + 8) + VT_SG * (10 + 3) + VT_SG * VT_STAGE_LD;
+    return 12 * ws + 3 * (4 * ws + 8) + (3 * ws / 2 + 2) + (3 * VT_QCAP + VT_QCAP / 2 + 8) + VT_SG * (20 + 3) + VT_SG * VT_STAGE_LD;
 }
 
 // The time-combined knot line of one particle: x(1) = Z1, x(k) = Z1 + (k - 0.5) H, x(p2) = ZN -- an
@@ -76,7 +76,7 @@ LT_DEV void vb_drain(const double* __restrict__ qa, const double* __restrict__ q
     __syncwarp();
 }
 
-#define VT_OWN_D 10                     // doubles / ints of one staged particle's own scalars
+#define VT_OWN_D 20                     // doubles / ints of one staged particle's own scalars
 #define VT_OWN_I 6
 
 template <class T, int PH>
@@ -133,12 +133,31 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
     for (int g0 = 0; g0 < 32; g0 += VT_SG) {
         const unsigned gm = (actmask >> g0) & ((1u << VT_SG) - 1u);
         if (gm == 0) continue;
-        {   // the group's owners park their scalars where every lane can read them
+        {   // the group's owners park their scalars where every lane can read them, together with everything of the
+            // fit that depends on the column's ends only and that the 32 lanes would otherwise each work out again:
+            // the knot line (Z1, ZN, H and the reciprocals of its three interval lengths), the sample line of the
+            // centre time, and the window origin (INTRVL of the start depth, tension:1287-1354)
             const int s = lane - g0;
-            if (s >= 0 && s < VT_SG) {
+            if (s >= 0 && s < VT_SG && ((gm >> s) & 1u)) {
                 double* o = od + s * VT_OWN_D; int* oq = oi + s * VT_OWN_I;
                 o[0] = o_w.t; o[1] = o_w.u; o[2] = o_w.w2; o[3] = o_w.w3; o[4] = o_zb; o[5] = o_zc; o[6] = o_zf; o[7] = o_depth; o[8] = o_pzc;
                 oq[0] = o_nd.x; oq[1] = o_nd.y; oq[2] = o_nd.z; oq[3] = o_nd.w; oq[4] = o_w.mode;
+                ColK oc; oc.zb = o_zb; oc.zc = o_zc; oc.zf = o_zf; oc.depth = o_depth; oc.h = -1.0 * o_depth;
+                double b1, c1, f1, bN, cN, fN;
+                zlev3<true>(D, oc, 0, b1, c1, f1); zlev3<true>(D, oc, L - 1, bN, cN, fN);
+                VbKnots K; K.p2 = P2;
+                K.Z1 = lag(D.LW4, b1, c1, f1); K.ZN = lag(D.LW4, bN, cN, fN); K.H = (K.ZN - K.Z1) * rp2;
+                const double rH = qrcp(K.H), dE1 = K.x(2) - K.x(1), dEN = K.x(P2) - K.x(P2 - 1), hsc = (cN - c1) * rp2;
+                o[9] = K.Z1; o[10] = K.ZN; o[11] = K.H; o[12] = rH; o[13] = qrcp(dE1); o[14] = qrcp(dEN); o[15] = dE1; o[16] = dEN;
+                o[17] = c1; o[18] = hsc; o[19] = qrcp(hsc);
+                int I0;
+                if (o_pzc < K.Z1) I0 = 1; else if (o_pzc > K.ZN) I0 = P2 - 1;
+                else {
+                    I0 = (int)floor((o_pzc - K.Z1) * rH + 0.5); I0 = max(1, min(P2 - 1, I0));
+                    while (I0 > 1 && o_pzc < K.x(I0)) --I0;
+                    while (I0 < P2 - 1 && !(o_pzc < K.x(I0 + 1))) ++I0;
+                }
+                oq[5] = max(1, min(I0 - VW / 2 + 1, P2 - VW + 1));             // knots [ka, ka + VW - 1]
             }
         }
         __syncwarp();
@@ -147,12 +166,13 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
             if (!((actmask >> p) & 1u)) continue;
             // ---- 0. the owner's scalars ---------------------------------------------------
             Stencil s0; s0.q = nullptr; s0.xp = 0.0; s0.yp = 0.0;
-            ColK col; double P_zc;
+            ColK col;
+            const double* o = od + pp * VT_OWN_D;
             {
-                const double* o = od + pp * VT_OWN_D; const int* oq = oi + pp * VT_OWN_I;
+                const int* oq = oi + pp * VT_OWN_I;
                 s0.nd = make_int4(oq[0], oq[1], oq[2], oq[3]); s0.w.mode = oq[4];
                 s0.w.t = o[0]; s0.w.u = o[1]; s0.w.w2 = o[2]; s0.w.w3 = o[3];
-                col.zb = o[4]; col.zc = o[5]; col.zf = o[6]; col.depth = o[7]; col.h = -1.0 * col.depth; P_zc = o[8];
+                col.zb = o[4]; col.zc = o[5]; col.zf = o[6]; col.depth = o[7]; col.h = -1.0 * col.depth;
             }
             // ---- 1. KH and depth of level l at the three hydro times (ver_turb:102-108) ----
             //         plus, per level, what the single-profile test below needs: the time-interpolated KH at the
@@ -176,10 +196,7 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
                 hs[t] = (zN - z1[t]) * rp2;
                 k1[t] = kc[t * L]; kN[t] = kc[t * L + L - 1];
             }
-            VbKnots K; K.p2 = P2;
-            K.Z1 = lag(D.LW4, z1[0], z1[1], z1[2]);
-            K.ZN = lag(D.LW4, zc[L - 1], zc[2 * L - 1], zc[3 * L - 1]);
-            K.H = (K.ZN - K.Z1) * rp2;
+            VbKnots K; K.p2 = P2; K.Z1 = o[9]; K.ZN = o[10]; K.H = o[11];
             // ---- 2-4, common case: ONE profile instead of three.  Without the clamps of ver_turb:264-268 the
             //         chain resample -> 8-point mean -> time polynomial -> (b + 4c + f)/6 is linear in the KH
             //         values, and with the levels at the same relative depths at the three hydro times
@@ -192,7 +209,7 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
             const bool single = __all_sync(VT_FULL, lev_ok) && shared_geom && k1[0] >= 0.0;
             if (single) {
                 const double* k4 = sl + L; const double* zt = zc + L;          // centre-time geometry
-                const double z1c = z1[1], hsc = hs[1], rhsc = qrcp(hsc);
+                const double z1c = o[17], hsc = o[18], rhsc = o[19];
                 // first sample at or above each level (the samples newx(j) = z1 + (j - 4) hs are an arithmetic
                 // progression: a quotient, checked against the sample's own formula); level 0 owns sample 5
                 for (int l = lane; l < L; l += 32) {
@@ -317,8 +334,7 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
             // ---- 5. chord slope of every interval, then the YPC1 knot slopes (tension:852-978).  Interior
             //         intervals have length H: their chord slope is a product and the three-point formula
             //         (DXIM1 SI + DXI SIM1)/(DXIM1 + DXI) the mean of the two chord slopes.
-            const double rH = qrcp(K.H), dE1 = K.x(2) - K.x(1), dEN = K.x(P2) - K.x(P2 - 1);
-            const double rE1 = qrcp(dE1), rEN = qrcp(dEN);
+            const double rH = o[12], rE1 = o[13], rEN = o[14], dE1 = o[15], dEN = o[16];
             for (int k = 1 + lane; k <= P2 - 1; k += 32) {
                 const double dy = fy[k + 1] - fy[k];
                 sk[k] = dy * (k == 1 ? rE1 : (k == P2 - 1 ? rEN : rH));
@@ -345,44 +361,46 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
             }
             __syncwarp();
             // ---- 6. window origin; SIGS on every interval (tension:314-782) -------------------
-            int I0;
-            {   // INTRVL of the start depth (tension:1287-1354)
-                if (P_zc < K.Z1) I0 = 1; else if (P_zc > K.ZN) I0 = P2 - 1;
-                else {
-                    I0 = (int)floor((P_zc - K.Z1) * rH + 0.5); I0 = max(1, min(P2 - 1, I0));
-                    while (I0 > 1 && P_zc < K.x(I0)) --I0;
-                    while (I0 < P2 - 1 && !(P_zc < K.x(I0 + 1))) ++I0;
-                }
-            }
-            const int ka = max(1, min(I0 - VW / 2 + 1, P2 - VW + 1));          // knots [ka, ka + VW - 1]
+            const int ka = oi[pp * VT_OWN_I + 5];                               // window origin: knots [ka, ka + VW - 1]
             double* st = stage + pp * VT_STAGE_LD;
+            // SIGS' classification of every interval (tension:480-527, 638-660).  Two tiers: a screen without
+            // divisions that is NECESSARY for an interval to need a solve -- convexity case with T > 2 (inside the
+            // window, where the tension factor is used) or with T within a whisker of LT_BAND (outside, where only
+            // the verdict of the Newton loop matters and it can fail only for T in LT_BAND, lt_step2.cuh);
+            // monotonicity case with S (3 S - S1 - S2) < 0 -- and, only in passes where some lane passes it, the
+            // exact tests and the queueing of the solves (convexity Newton loop, monotonicity secant loop), which
+            // run 32 at a time.
             for (int k0 = 1; k0 <= P2 - 1; k0 += 32) {
                 const int k = k0 + lane, kk = min(k, P2 - 1);
                 const bool live = k <= P2 - 1, inwin = live && k >= ka && k <= ka + VW - 2;
-                // SIGS' classification of one interval (tension:480-527, 638-660) in straight-line form; the
-                // rare solves (convexity Newton loop, monotonicity secant loop) are queued and run 32 at a time
                 const double S = sk[kk], S1 = yp[kk], S2 = yp[kk + 1];
                 const double D1 = S - S1, D2 = S2 - S, D1D2 = D1 * D2;
-                const bool big = (D1D2 == 0.0 && S1 != S2) || (S == 0.0 && S1 * S2 > 0.0);           // SIGMA = SBIG
-                const double a = fabs(D1), b = fabs(D2), hi = a > b ? a : b, lo = a > b ? b : a;
-                const double Tq = qdiv(hi, lo);                                // = MAX(D1/D2, D2/D1) when D1 D2 > 0
-                const double T0 = 3.0 * S - S1 - S2, D0 = T0 * T0 - S1 * S2;
-                // the convexity solve: its value is needed inside the window; outside only its verdict, and
-                // the loop can fail only for T in LT_BAND (lt_step2.cuh)
-                const bool conv = !big && D1D2 > 0.0 && hi > 2.0 * lo && Tq > 2.0 && (inwin || (Tq > LT_BAND_LO && Tq < LT_BAND_HI));
-                const bool mono = !big && D1D2 < 0.0 && !(S1 * S < 0.0 || S2 * S < 0.0) && !(D0 <= 0.0 || S * T0 >= 0.0);
+                // SIGMA = SBIG: D1 D2 = 0 with S1 /= S2, or S = 0 with S1 S2 > 0 (then D1 D2 = -S1 S2 exactly)
+                const bool big = (D1D2 == 0.0 && S1 != S2) || (S == 0.0 && D1D2 < 0.0);
+                const double a = fabs(D1), b = fabs(D2), T0 = 3.0 * S - S1 - S2;
+                const double flo = inwin ? 2.0 : 2.0199, fhi = inwin ? 1.0e300 : 2.0601;       // MAX(D1/D2, D2/D1) in (flo, fhi)
                 const bool use = live && (inwin || !window_only);
-                const int pend = use ? (conv ? 1 : (mono ? 2 : 0)) : 0;
-                if (inwin && !pend) st[2 * VW + (k - ka)] = big ? 85.0 : 0.0;
-                const unsigned pm = __ballot_sync(VT_FULL, pend != 0);
-                if (pend) {
-                    const int pos = qlen + __popc(pm & ((1u << lane) - 1u));
-                    qa[pos] = conv ? Tq : S; qb[pos] = S1; qc[pos] = S2;
-                    qtag[pos] = ((pend - 1) << 24) | (pp << 16) | (inwin ? (k - ka) : 0xffff);
+                const bool cand_c = D1D2 > 0.0 && ((a > flo * b && a < fhi * b) || (b > flo * a && b < fhi * a));
+                const bool cand_m = D1D2 < 0.0 && S * T0 < 0.0;
+                int pend = 0;
+                if (__any_sync(VT_FULL, use && (cand_c || cand_m))) {
+                    const double hi = a > b ? a : b, lo = a > b ? b : a;
+                    const double Tq = qdiv(hi, lo);                            // = MAX(D1/D2, D2/D1) when D1 D2 > 0
+                    const double D0 = T0 * T0 - S1 * S2;
+                    const bool conv = cand_c && Tq > 2.0 && (inwin || (Tq > LT_BAND_LO && Tq < LT_BAND_HI));
+                    const bool mono = cand_m && !(S1 * S < 0.0 || S2 * S < 0.0) && !(D0 <= 0.0);
+                    pend = use ? (conv ? 1 : (mono ? 2 : 0)) : 0;
+                    const unsigned pm = __ballot_sync(VT_FULL, pend != 0);
+                    if (pend) {
+                        const int pos = qlen + __popc(pm & ((1u << lane) - 1u));
+                        qa[pos] = conv ? Tq : S; qb[pos] = S1; qc[pos] = S2;
+                        qtag[pos] = ((pend - 1) << 24) | (pp << 16) | (inwin ? (k - ka) : 0xffff);
+                    }
+                    qlen += __popc(pm);
+                    __syncwarp();
+                    if (qlen >= 32) { vb_drain(qa, qb, qc, qtag, qlen - 32, 32, stage, errm); qlen -= 32; }
                 }
-                qlen += __popc(pm);
-                __syncwarp();
-                if (qlen >= 32) { vb_drain(qa, qb, qc, qtag, qlen - 32, 32, stage, errm); qlen -= 32; }
+                if (inwin && !pend) st[2 * VW + (k - ka)] = big ? 85.0 : 0.0;
             }
             for (int q = lane; q < VW; q += 32) {
                 const bool in = ka + q <= P2;
