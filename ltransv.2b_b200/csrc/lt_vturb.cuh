@@ -329,8 +329,8 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
                         fy[k] = fma(fma(-6.0, q6, a6), 0.16666666666666666, q6);
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();                                                      // knot values complete; samples and column dead
             // ---- 5. chord slope of every interval, then the YPC1 knot slopes (tension:852-978).  Interior
             //         intervals have length H: their chord slope is a product and the three-point formula
             //         (DXIM1 SI + DXI SIM1)/(DXIM1 + DXI) the mean of the two chord slopes.
