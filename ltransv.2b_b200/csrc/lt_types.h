@@ -63,6 +63,10 @@ struct LtDev {
     // vw[row][i]: rows 0..VW-1 knot values, VW..2VW-1 knot slopes, 2VW..3VW-1 tension factors of the
     // window of chunk-local particle i; vz1 / vzn the knot line; vka = first knot | SigErr << 16
     double *vw, *vz1, *vzn; int* vka; int vw_stride;
+    // the order in which the VTurb kernels visit the slots (finer depth bins than the slot order itself, see
+    // resort() in ltrans_b200.cu); nullptr = slot order
+    const int* vorder;
+    int vb_slot_order;          // 1: k_vbuild keeps the slot order (scratch column = slot), only k_vwalk follows vorder
     // Lagrange form of the 3-point time polynomial (interpolation_module.f90:70-107),
     // LW[v][t] = weight of hydro record t (b,c,f) at internal time ix(v), with the p == 1
     // triplet (b,b,c) folded in; LW4 = (LW[0] + 4 LW[1] + LW[2]) / 6; LWz = raw weights at ix(2)

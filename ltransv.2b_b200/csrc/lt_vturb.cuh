@@ -103,8 +103,9 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
     double* sk = ys;                    // [P2 + 2] chord slope of interval (k, k + 1), over B (dead after step 4)
     double* yp = sk + (P2 + 2);         // [P2 + 2] knot slopes                                            (YPKc)
 
-    const int n = warp_first + lane;
-    const bool valid = n < base + count;
+    const int ci = warp_first - base + lane;                           // index within the chunk (scratch column)
+    const bool valid = ci < count;
+    const int n = !valid ? 0 : (D.vorder && !D.vb_slot_order ? D.vorder[base + ci] : base + ci);   // the particle's slot
     const bool act = valid && D.s_act[n] != 0;
     // this lane's own particle: what the other lanes need to fit its column
     int4 o_nd = make_int4(0, 0, 0, 0); Wt o_w; o_w.mode = 1; o_w.t = o_w.u = o_w.w2 = o_w.w3 = 0.0;
@@ -408,8 +409,7 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
                 if (ka + q >= P2 || q == VW - 1) st[2 * VW + q] = 0.0;        // no interval starts at the last knot
             }
             if (lane == p) {                                                   // the owner keeps its knot line
-                const int i = n - base;
-                D.vz1[i] = K.Z1; D.vzn[i] = K.ZN;
+                D.vz1[ci] = K.Z1; D.vzn[ci] = K.ZN;
             }
             if (lane == 0) kas[pp] = ka;
             __syncwarp();                                                      // A and B are overwritten by the next column
@@ -418,7 +418,7 @@ LT_DEV void vbuild_warp(const LtDev& D, double* __restrict__ sm, int warp_first,
         if (qlen > 0) { vb_drain(qa, qb, qc, qtag, 0, qlen, stage, errm); qlen = 0; }
         {
             const int s = lane - g0;
-            if (s >= 0 && s < VT_SG && ((gm >> s) & 1u)) D.vka[n - base] = kas[s] | (((*errm >> s) & 1) << 16);
+            if (s >= 0 && s < VT_SG && ((gm >> s) & 1u)) D.vka[ci] = kas[s] | (((*errm >> s) & 1) << 16);
         }
         // row-major scratch: VT_SG consecutive particles per row
         for (int e = lane; e < VT_SG * 3 * VW; e += 32) {
@@ -506,10 +506,9 @@ LT_DEV double hval_c(const IvC& c, double T)
 }
 
 template <class T, int PH>
-LT_DEV void vwalk_particle(const LtDev& D, int n, int base)
-{
+LT_DEV void vwalk_particle(const LtDev& D, int n, int i)
+{   // n = slot, i = index within the chunk (scratch column)
     if (!D.s_act[n]) return;
-    const int i = n - base;
     const double background = (double)1.0E-6f;                          // ledger 2
     const double P_zc = D.s_pzc[n], P_depth = D.s_depth[n], P_zetac = D.s_zec[n];
     const int p2 = 4 * D.P.ws;
@@ -623,10 +622,9 @@ LT_DEV float hval_f(const IvF& c, float U)
 }
 
 template <class T, int PH>
-LT_DEV void vwalk_particle_f32(const LtDev& D, int n, int base)
+LT_DEV void vwalk_particle_f32(const LtDev& D, int n, int i)
 {
     if (!D.s_act[n]) return;
-    const int i = n - base;
     const float background = 1.0E-6f;                                   // ledger 2
     const double P_zc = D.s_pzc[n], P_depth = D.s_depth[n], P_zetac = D.s_zec[n];
     const int p2 = 4 * D.P.ws;

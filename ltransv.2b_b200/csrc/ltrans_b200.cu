@@ -93,16 +93,16 @@ __global__ void __launch_bounds__(LT_BLK_VB, MINB) k_vbuild(const __grid_constan
 template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_VW, LT_MIN_VW) k_vwalk(const __grid_constant__ LtDev D, int base, int count)
 {
-    const int n = base + blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     lev_tables_load(D);                                                 // the refit of a walked-out window
-    if (n < base + count) vwalk_particle<T, PH>(D, n, base);
+    if (i < count) { const int n = D.vorder ? D.vorder[base + i] : base + i; vwalk_particle<T, PH>(D, n, D.vb_slot_order ? n - base : i); }
 }
 template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_VW, LT_MIN_VW) k_vwalk_f32(const __grid_constant__ LtDev D, int base, int count)
 {
-    const int n = base + blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     lev_tables_load(D);
-    if (n < base + count) vwalk_particle_f32<T, PH>(D, n, base);
+    if (i < count) { const int n = D.vorder ? D.vorder[base + i] : base + i; vwalk_particle_f32<T, PH>(D, n, D.vb_slot_order ? n - base : i); }
 }
 template <class T, int PH>
 __global__ void __launch_bounds__(LT_BLK_FIN, LT_MIN_FIN) k_finish(const __grid_constant__ LtDev D)
@@ -145,7 +145,9 @@ __global__ void k_fill_slot(const TI* __restrict__ in, const uint8_t* __restrict
 // element-major key once per external step 128 M; depth-major once per external step 132 M,
 // every 10 / 5 / 2 / 1 steps 141 / 146 / 153 / 157 M; 32 bins and the fused move 163 M.  At Gulf
 // scale (ws = 37, 12.5 M particles) depth-major takes `k_vturb` from 64 to 41 ms per step.
-// LTGPU_SORT=0 disables, LTGPU_SORT_MODE=<bins> (0 = element-major), LTGPU_SORT_EVERY=<steps>.
+// From 2 M particles on the slots take 8 bins and the VTurb kernels their own visiting order of 64 bins (resort()).
+// LTGPU_SORT=0 disables, LTGPU_SORT_MODE=<bins> (0 = element-major), LTGPU_VT_BINS=<bins> (0 = slot order),
+// LTGPU_SORT_EVERY=<steps>.
 __global__ void k_sort_keys(const LtDev D, unsigned* __restrict__ key, int* __restrict__ idx, int bins)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,7 +337,8 @@ struct ltgpu_ctx {
     bool have_grid = false, have_bounds = false, have_particles = false, have_habitat = false;
     int nthreads_grid = 0;
     // re-sort state
-    bool sort_on = true; int sort_mode = 32, sort_every = 1;
+    bool sort_on = true; int sort_mode = 32, sort_every = 1, vt_bins = 0, sort_mode_cfg = -1, vt_bins_cfg = -1;   // slot order / VTurb visiting order (resort); cfg -1: by particle count
+    int* d_vorder = nullptr;
     unsigned *d_key = nullptr, *d_key2 = nullptr; int *d_idx = nullptr, *d_perm = nullptr, *d_pid = nullptr;
     void* d_cub = nullptr; size_t cub_bytes = 0;
     double* spare8 = nullptr; double* out8 = nullptr;          // bounce buffers of ltgpu_fetch
@@ -556,6 +559,23 @@ static int32_t resort(ltgpu_ctx* ctx)
     D.behave = (int8_t*)beh;
     D.pid = ctx->d_pid;
     ctx->launches += 3;
+    // The kernels want different neighbours.  k_advect / k_finish gain from lanes in the same or adjacent
+    // ELEMENTS (field windows and element records shared through L1 / L2): few depth bins.  k_vwalk gains from
+    // lanes at the same RELATIVE DEPTH (spline interval changes, tension regimes, boundary clamps in step):
+    // many bins; k_vbuild fits one column per warp and follows either.  So the slots are ordered by
+    // (sort_mode bins, element) and the VTurb kernels visit them through a second index ordered by
+    // (vt_bins, element).  Measured at 12.5 M particles with one order for all: 8 bins k_advect 26.2 ms,
+    // VTurb 52.6; 32 bins 28.6 / 50.5; 64 bins 30.8 / 49.9.
+    if (ctx->d_vorder && ctx->prm.VTurbOn && !ctx->vt_legacy) {
+        k_sort_keys<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_key, ctx->d_idx, ctx->vt_bins);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_vorder, n, 0, ctx->key_bits, ctx->compute));
+        D.vorder = ctx->d_vorder;
+        // k_vbuild fits one column per warp: lane coherence means nothing to it, but consecutive slots in the same
+        // element re-use the KH columns through L1 / L2.  It keeps the slot order (scratch column = slot) when one
+        // chunk holds all particles; only k_vwalk follows vorder (VTurb 50.2 -> 48.9 ms at 12.5 M particles).
+        { const char* e = getenv("LTGPU_VB_SLOT_ORDER"); D.vb_slot_order = (!(e && e[0] == '0') && ctx->vt_chunk >= n) ? 1 : 0; }
+        ctx->launches += 2;
+    }
     CK(cudaGetLastError());
     ctx->sorts++;
     return LTGPU_OK;
@@ -706,7 +726,9 @@ int32_t ltgpu_create(const ltgpu_params* prm, int32_t device, ltgpu_ctx** out)
     ctx->sort_on = !(so && so[0] == '0');
     { const char* vd = getenv("LTGPU_VB_DEEP"); if (vd) ctx->vb_deep = atoi(vd); }
     { const char* se = getenv("LTGPU_SORT_EVERY"); if (se && atoi(se) > 0) ctx->sort_every = atoi(se); }
-    { const char* sm = getenv("LTGPU_SORT_MODE"); ctx->sort_mode = sm ? std::max(0, std::min(127, atoi(sm))) : 32; }
+    // -1: chosen by ltgpu_set_particles from the particle count
+    { const char* sm = getenv("LTGPU_SORT_MODE"); ctx->sort_mode_cfg = sm ? std::max(0, std::min(127, atoi(sm))) : -1; }
+    { const char* vb = getenv("LTGPU_VT_BINS"); ctx->vt_bins_cfg = vb ? std::max(0, std::min(127, atoi(vb))) : -1; }   // 0: VTurb in slot order
     { const char* vl = getenv("LTGPU_VTURB_LEGACY"); ctx->vt_legacy = vl && vl[0] == '1'; }     // round-1 fused k_vturb (A/B only)
     { const char* ec = getenv("LTGPU_EVCAP"); ctx->evcap = ec && atoi(ec) > 0 ? atoi(ec) : 0; }   // 0: sized by set_particles
     *out = ctx;
@@ -994,6 +1016,21 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
         ctx->vt_chunk = chunk; D.vw_stride = chunk;
         TRY(dalloc(ctx, &D.vw, (size_t)3 * VW * chunk)); TRY(dalloc(ctx, &D.vz1, (size_t)chunk)); TRY(dalloc(ctx, &D.vzn, (size_t)chunk));
         TRY(dalloc(ctx, &D.vka, (size_t)chunk));
+    }
+    {   // Two orders (slots by 8 depth bins x element, VTurb visiting order by 64 bins x element) pay when the
+        // fields do not fit L2 - k_advect's windows then come from DRAM unless neighbouring lanes share them - and
+        // there are enough particles to carry the second radix sort (0.1 ms per step): +3.4 % at 12.5 M particles
+        // on the Gulf grid (1.9 GB of u, v, w, AKs).  With L2-resident fields lanes at the same relative depth are
+        // worth more to k_advect than lanes in the same element: -8 % at 10 M particles on 120x80x20, -1.5 % at
+        // 1 M on 130x130x20.  There: one order, 32 bins.
+        int l2 = 0; cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
+        const size_t field_bytes = (size_t)ctx->rho_nodes * (size_t)ctx->prm.ws * 4 * ctx->esz * 4;
+        const bool big = n >= (1 << 21) && field_bytes > (size_t)l2;
+        ctx->sort_mode = ctx->sort_mode_cfg >= 0 ? ctx->sort_mode_cfg : (big ? 8 : 32);
+        ctx->vt_bins = ctx->vt_bins_cfg >= 0 ? ctx->vt_bins_cfg : (big ? 64 : 0);
+        D.vorder = nullptr; ctx->d_vorder = nullptr;
+        if (ctx->sort_on && ctx->prm.VTurbOn && !ctx->vt_legacy && ctx->vt_bins > 0 && ctx->vt_bins != ctx->sort_mode)
+            TRY(dalloc(ctx, &ctx->d_vorder, N));
     }
     k_iota<<<(n + 255) / 256, 256, 0, ctx->compute>>>(ctx->d_pid, n);
     D.pid = ctx->d_pid;
