@@ -1025,7 +1025,7 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
         // 1 M on 130x130x20.  There: one order, 32 bins.
         int l2 = 0; cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, ctx->device);
         const size_t field_bytes = (size_t)ctx->rho_nodes * (size_t)ctx->prm.ws * 4 * ctx->esz * 4;
-        const bool big = n >= (1 << 21) && field_bytes > (size_t)l2;
+        const bool big = n >= (1 << 20) && field_bytes > (size_t)l2;
         ctx->sort_mode = ctx->sort_mode_cfg >= 0 ? ctx->sort_mode_cfg : (big ? 8 : 32);
         ctx->vt_bins = ctx->vt_bins_cfg >= 0 ? ctx->vt_bins_cfg : (big ? 64 : 0);
         D.vorder = nullptr; ctx->d_vorder = nullptr;

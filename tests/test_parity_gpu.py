@@ -483,6 +483,29 @@ def test_vturb_chunked_scratch_is_invisible(monkeypatch):
     assert np.array_equal(sa, sb)
 
 
+def test_slot_order_and_vturb_visiting_order_are_invisible(monkeypatch):
+    """At Gulf scale the slots are ordered by (8 depth bins, element) and k_vwalk visits them through a second index
+    ordered by (64 bins, element), k_vbuild in slot order when one scratch chunk holds all particles, else in the
+    walk's order.  Particles do not interact and Philox is keyed by particle id: every combination gives the same
+    bits as one order for all and as no re-sort at all."""
+    for k in ("LTGPU_SORT", "LTGPU_SORT_MODE", "LTGPU_VT_BINS", "LTGPU_VB_SLOT_ORDER"):
+        monkeypatch.delenv(k, raising=False)
+    for wk in (SMALL, GULF):
+        ref, sref = _vturb_run(monkeypatch, 3000, {"LTGPU_SORT": "0"}, world_kw=wk)
+        monkeypatch.delenv("LTGPU_SORT", raising=False)
+        for env in ({"LTGPU_SORT_MODE": "8", "LTGPU_VT_BINS": "64"},
+                    {"LTGPU_SORT_MODE": "8", "LTGPU_VT_BINS": "64", "LTGPU_VB_SLOT_ORDER": "0"},
+                    {"LTGPU_SORT_MODE": "8", "LTGPU_VT_BINS": "64", "LTGPU_VTURB_CHUNK": "416"},
+                    {"LTGPU_SORT_MODE": "0", "LTGPU_VT_BINS": "127"},
+                    {"LTGPU_SORT_MODE": "32", "LTGPU_VT_BINS": "0"}):
+            f, sg = _vturb_run(monkeypatch, 3000, env, world_kw=wk)
+            for k in ("x", "y", "z", "status", "r_ele", "age"):
+                assert np.array_equal(ref[k], f[k]), (env, k)
+            assert np.array_equal(sref, sg), env
+            for k in env:
+                monkeypatch.delenv(k, raising=False)
+
+
 def _first_divergence(w, prm, n, nexternal, habitat=None, tol=1e-9):
     """CUDA and oracle side by side for nexternal external steps, compared after EVERY internal step.
     Returns (first step with a deviation > tol per particle or -1, whether the two SigErr fall-back
