@@ -148,7 +148,10 @@ __global__ void k_fill_slot(const TI* __restrict__ in, const uint8_t* __restrict
 // From 2 M particles on the slots take 8 bins and the VTurb kernels their own visiting order of 64 bins (resort()).
 // LTGPU_SORT=0 disables, LTGPU_SORT_MODE=<bins> (0 = element-major), LTGPU_VT_BINS=<bins> (0 = slot order),
 // LTGPU_SORT_EVERY=<steps>.
-__global__ void k_sort_keys(const LtDev D, unsigned* __restrict__ key, int* __restrict__ idx, int bins)
+// Key of the depth-major orders: (bin << ebits) | element with ebits = bits of the element count, idle particles in
+// bin `bins` (one past the last): as few key bits as the grid needs, so the radix sort runs 3 passes of 8 bits
+// instead of 4 at Gulf scale (20 + 4 bits).
+__global__ void k_sort_keys(const LtDev D, unsigned* __restrict__ key, int* __restrict__ idx, int bins, int ebits)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= D.n) return;
@@ -157,11 +160,13 @@ __global__ void k_sort_keys(const LtDev D, unsigned* __restrict__ key, int* __re
     double h = 0.25 * (__ldg(D.depth + nd.x) + __ldg(D.depth + nd.y) + __ldg(D.depth + nd.z) + __ldg(D.depth + nd.w));
     bool idle = (D.flags[n] & (LT_F_SETTLED | LT_F_DEAD | LT_F_OOB)) != 0;
     idx[n] = n;
-    if (idle) { key[n] = 0xffffffffu; return; }                             // inactive particles go last
     if (bins > 0) {
         int b = (int)(-(double)bins * D.z[n] / fmax(h, 1e-3)); b = max(0, min(bins - 1, b));
-        key[n] = ((unsigned)b << 24) | ((unsigned)re & 0xffffffu);          // up to 127 bins, 16.7 M elements
-    } else {
+        key[n] = ((unsigned)(idle ? bins : b) << ebits) | (unsigned)max(re, 0);   // inactive particles go last
+        return;
+    }
+    if (idle) { key[n] = 0xffffffffu; return; }
+    {
         int b = (int)(-8.0 * D.z[n] / fmax(h, 1e-3)); b = max(0, min(7, b));
         key[n] = ((unsigned)re << 3) | (unsigned)b;
     }
@@ -338,7 +343,7 @@ struct ltgpu_ctx {
     int nthreads_grid = 0;
     // re-sort state
     bool sort_on = true; int sort_mode = 32, sort_every = 1, vt_bins = 0, sort_mode_cfg = -1, vt_bins_cfg = -1;   // slot order / VTurb visiting order (resort); cfg -1: by particle count
-    int* d_vorder = nullptr;
+    int* d_vorder = nullptr; int ebits = 24, bbits_slot = 8, bbits_vt = 8;   // key layout of k_sort_keys
     unsigned *d_key = nullptr, *d_key2 = nullptr; int *d_idx = nullptr, *d_perm = nullptr, *d_pid = nullptr;
     void* d_cub = nullptr; size_t cub_bytes = 0;
     double* spare8 = nullptr; double* out8 = nullptr;          // bounce buffers of ltgpu_fetch
@@ -542,8 +547,8 @@ __global__ void k_permute_all(const __grid_constant__ PermArgs a, const int* __r
 static int32_t resort(ltgpu_ctx* ctx)
 {
     LtDev& D = ctx->D; int n = D.n;
-    k_sort_keys<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_key, ctx->d_idx, ctx->sort_mode);
-    CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_perm, n, 0, ctx->key_bits, ctx->compute));
+    k_sort_keys<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_key, ctx->d_idx, ctx->sort_mode, ctx->ebits);
+    CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_perm, n, 0, ctx->sort_mode > 0 ? ctx->ebits + ctx->bbits_slot : 32, ctx->compute));
     double** a8[LT_NP8] = {&D.x, &D.y, &D.z, &D.age, &D.dob, &D.lifespan, &D.psalt, &D.ptemp, &D.timer, &D.sprev, &D.zprev};
     int** a4[LT_NP4] = {&D.r_ele, &D.u_ele, &D.v_ele, &D.hitB, &D.hitL, &D.endpoly, &D.nsig, &ctx->d_pid};
     uint8_t* beh = (uint8_t*)D.behave;
@@ -567,8 +572,10 @@ static int32_t resort(ltgpu_ctx* ctx)
     // (vt_bins, element).  Measured at 12.5 M particles with one order for all: 8 bins k_advect 26.2 ms,
     // VTurb 52.6; 32 bins 28.6 / 50.5; 64 bins 30.8 / 49.9.
     if (ctx->d_vorder && ctx->prm.VTurbOn && !ctx->vt_legacy) {
-        k_sort_keys<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_key, ctx->d_idx, ctx->vt_bins);
-        CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_vorder, n, 0, ctx->key_bits, ctx->compute));
+        k_sort_keys<<<(n + 255) / 256, 256, 0, ctx->compute>>>(D, ctx->d_key, ctx->d_idx, ctx->vt_bins, ctx->ebits);
+        // the slots were just ordered by (few bins, element) and the radix sort is stable: one pass over the bin
+        // byte alone leaves them ordered by (vt_bins, element)
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_vorder, n, ctx->sort_mode > 0 ? ctx->ebits : 0, ctx->ebits + ctx->bbits_vt, ctx->compute));
         D.vorder = ctx->d_vorder;
         // k_vbuild fits one column per warp: lane coherence means nothing to it, but consecutive slots in the same
         // element re-use the KH columns through L1 / L2.  It keeps the slot order (scratch column = slot) when one
@@ -1035,9 +1042,10 @@ int32_t ltgpu_set_particles(ltgpu_ctx* ctx, int32_t n, int64_t first_id,
     k_iota<<<(n + 255) / 256, 256, 0, ctx->compute>>>(ctx->d_pid, n);
     D.pid = ctx->d_pid;
     {
-        int bits = 3; while ((1ll << bits) < ((long long)(D.R.nE + 1) << 3)) ++bits;
-        ctx->key_bits = 32;                               // idle particles use key 0xffffffff
-        (void)bits;
+        auto nbits = [](long long v) { int b = 1; while ((1ll << b) <= v) ++b; return b; };   // bits that hold 0 .. v
+        ctx->ebits = nbits(D.R.nE); ctx->bbits_slot = nbits(std::max(ctx->sort_mode, 1)); ctx->bbits_vt = nbits(std::max(ctx->vt_bins, 1));
+        if (ctx->ebits + std::max(ctx->bbits_slot, ctx->bbits_vt) > 32) return LTGPU_E_ARG;      // > 2^24 elements with 127 bins
+        ctx->key_bits = 32;
         cub::DeviceRadixSort::SortPairs(nullptr, ctx->cub_bytes, ctx->d_key, ctx->d_key2, ctx->d_idx, ctx->d_perm, n, 0, ctx->key_bits, ctx->compute);
         void* q = nullptr; CK(cudaMalloc(&q, std::max<size_t>(ctx->cub_bytes, 16))); ctx->owned.push_back(q); ctx->d_cub = q;
     }
