@@ -1,31 +1,31 @@
-// lt_step2.cuh -- the production step: three kernels per internal time step, one
-// thread per particle, per-particle scratch (SoA, 121 B) handed from one to the next.
+// lt_step2.cuh -- the production step: the kernels of one internal time step, one thread per
+// particle except the VTurb fit (lt_vturb.cuh), per-particle scratch (SoA) handed from one to the next.
 //
 //   k_advect : gates, setEle, setInterp, vertical clamp, RK4 advection (find_currents x4),
 //              salinity / temperature, HTurb                      LTRANS.f90:778-1087
-//   k_vturb  : Visser random displacement model                   ver_turb_module.f90:30-380
+//   k_vbuild : the water-column fit of the Visser random displacement model, one column per warp
+//   k_vwalk  : its 60 sub-steps (both in lt_vturb.cuh)            ver_turb_module.f90:30-380
 //   k_finish : behave, vertical + horizontal reflection, bounds checks, commit, setEle at
 //              the new position, settlement                        LTRANS.f90:1110-1382
+//   (k_vturb, the round-1 per-thread VTurb kernel built on VtCtx below, is kept as the A/B reference
+//    of the tests: LTGPU_VTURB_LEGACY=1; VtCtx::build also serves k_vwalk's rare window refit)
 //
-// Why three: the three phases have very different register / instruction footprints
+// Why several: the phases have very different register / instruction footprints
 // (the fused v1 kernel stalled on instruction fetch half of the time, see
 // profiles/r01_notes.md); split, each keeps its own occupancy and i-cache working set.
 //
 // Differences from the reference that stay inside the 1e-9 parity budget (they change
-// results by O(1e-16) relative):
+// results by O(1e-16) relative; DESIGN.md section 6 has the full list):
 //   * the 3-point time polynomial is applied as Lagrange weights computed once per step
 //     on the host (LtDev::LW) instead of polintd's divided differences per value;
 //   * reciprocals come from qrcp()/qdiv() (<= 1 ulp) in the smooth numerics;
-//   * VTurb: the 84 spline knots are uniform in the interior (an identity of the
+//   * VTurb: the 4 ws spline knots are uniform in the interior (an identity of the
 //     reference's construction: movex(i) = z1 + (i - 0.5) R / p2), so abscissae are
-//     evaluated, not stored; KH knot values are built only in a 32-knot window around
-//     the particle and re-centred on demand; end slopes (YPC1) and the tension factor
-//     (SIGS) are solved only for the interval being evaluated -- every one of those is
-//     a local function of its neighbours in the reference, so windowing changes nothing;
-//     the 8-point moving average is a running sum.
+//     evaluated, not stored;
 //   * SigErr (Newton did not converge in 10000 iterations in SOME interval of the column,
-//     which makes the reference fall back to linint for the whole column) is only seen
-//     for the interval being evaluated.
+//     which makes the reference fall back to linint for the whole column) is examined on
+//     every interval of the fit by k_vbuild, as the reference does; the legacy VtCtx path
+//     does so only with its sweep() (vturb_window_sigs = 0).
 #pragma once
 #include "lt_device.cuh"
 
