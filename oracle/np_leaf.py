@@ -353,6 +353,106 @@ def hpval(t, x, y, yp, sigma):
     return s + (tm * ((e2 - e1) * (d1 + d2) + tm * (d1 - d2)) + sig * ((e1 * ems - e2) * d1 + (e1 - e2 * ems) * d2)) / e
 
 
+# --------------------------------------------------------------------- ver_turb_module.f90
+def _f32(v):
+    """a single-precision literal as the double it widens to"""
+    import struct
+    return struct.unpack("f", struct.pack("f", v))[0]
+
+
+def vturb_column(ws, idt, p, ex, ix, khb, khc, khf, wzb, wzc, wzf, P_zc, P_depth, P_zetac, dev):
+    """ver_turb_module.f90:30-380 from step ii. on (the KH gather of step i. is the caller's): the column fit and the
+    random displacement loop for one particle, `dev` = the idt/2 normal deviates norm() would return, in draw
+    order.  Written from the Fortran with 1-based lists (index 0 unused).  -> (TurbV, SigErr)"""
+    background = _f32(1.0e-6)                                            # :43 REAL(4) PARAMETER
+    p2 = ws * 4                                                          # :63
+    one = lambda a: [None] + list(a)                                     # 1-based view
+    KHb, KHc, KHf, Wb, Wc, Wf = one(khb), one(khc), one(khf), one(wzb), one(wzc), one(wzf)
+    # ii.a :116-124 (float(j-4) is REAL(4): exact for these integers)
+    newx = {}
+    for t, W in (("b", Wb), ("c", Wc), ("f", Wf)):
+        nx = [0.0] * (p2 + 8)
+        for j in range(1, p2 + 8):
+            nx[j] = W[1] + float(j - 4) * (W[ws] - W[1]) / float(p2)
+        newx[t] = nx
+    # :126-133
+    slope, icpt = {}, {}
+    for t, K, W in (("b", KHb, Wb), ("c", KHc, Wc), ("f", KHf, Wf)):
+        sl, ic = [0.0] * ws, [0.0] * ws
+        for i in range(1, ws):
+            sl[i] = (K[i] - K[i + 1]) / (W[i] - W[i + 1])
+            ic[i] = K[i] - sl[i] * W[i]
+        slope[t], icpt[t] = sl, ic
+    # :135-166 the walking jlo
+    newy = {}
+    for t, W in (("b", Wb), ("c", Wc), ("f", Wf)):
+        ny = [0.0] * (p2 + 8)
+        jlo = 1
+        for j in range(5, p2 + 4):
+            while not (W[jlo + 1] > newx[t][j]):
+                jlo += 1
+            ny[j] = slope[t][jlo] * newx[t][j] + icpt[t][jlo]
+        newy[t] = ny
+    # ii.b :173-180: the lower pads take KHb(1) at all three times
+    for i in range(1, 5):
+        newy["b"][i] = KHb[1]; newy["c"][i] = KHb[1]; newy["f"][i] = KHb[1]
+        newy["b"][i + p2 + 3] = KHb[ws]; newy["c"][i + p2 + 3] = KHc[ws]; newy["f"][i + p2 + 3] = KHf[ws]
+    # iii. :187-197, iv. :200-213
+    movex, movey = {}, {}
+    for t, K, W in (("b", KHb, Wb), ("c", KHc, Wc), ("f", KHf, Wf)):
+        mx, my = [0.0] * (p2 + 2), [0.0] * (p2 + 2)
+        ny, nx = newy[t], newx[t]
+        for i in range(2, p2):
+            my[i] = (ny[i] + ny[i + 1] + ny[i + 2] + ny[i + 3] + ny[i + 4] + ny[i + 5] + ny[i + 6] + ny[i + 7]) / 8.0
+            mx[i] = nx[i] + (nx[i + 7] - nx[i]) / 2.0
+        mx[1] = W[1]; my[1] = K[1]; mx[p2] = W[ws]; my[p2] = K[ws]
+        movex[t], movey[t] = mx, my
+    # v. :223-262, clamps :264-268, vi. :272-275
+    ifitx, ifity = [0.0] * p2, [0.0] * p2                                # 0-based: handed to the spline routines
+    for k in range(1, p2 + 1):
+        if p == 1:
+            eyx = [movex["b"][k], movex["b"][k], movex["c"][k]]; eyy = [movey["b"][k], movey["b"][k], movey["c"][k]]
+        else:
+            eyx = [movex["b"][k], movex["c"][k], movex["f"][k]]; eyy = [movey["b"][k], movey["c"][k], movey["f"][k]]
+        xb, xc, xf = polintd(ex, eyx, ix[0]), polintd(ex, eyx, ix[1]), polintd(ex, eyx, ix[2])
+        yb, yc, yf = polintd(ex, eyy, ix[0]), polintd(ex, eyy, ix[1]), polintd(ex, eyy, ix[2])
+        if yb < 0.0:
+            yb = 0.0
+        if yc < 0.0:
+            yc = 0.0
+        if yf < 0.0:
+            yf = 0.0
+        ifity[k - 1] = (yb + 4.0 * yc + yf) / 6.0
+        ifitx[k - 1] = (xb + 4.0 * xc + xf) / 6.0
+    # vii. :278-279
+    ypk, sigk, ier, sigerr = tspsi(ifitx, ifity)
+    # viii. - x. :282-337
+    deltat = 2.0
+    loop = idt // int(deltat)
+    ParZc = P_zc
+    for i in range(1, loop + 1):
+        if ParZc < P_depth or ParZc > P_zetac:
+            Kprimec = 0.0
+        elif sigerr == 0:
+            Kprimec = hpval(ParZc, ifitx, ifity, ypk, sigk)
+        else:
+            _, Kprimec = linint(ifitx, ifity, ParZc)
+        KprimeZc = -1.0 * Kprimec * deltat
+        Z3rdc = ParZc + 0.5 * KprimeZc
+        if Z3rdc < P_depth or Z3rdc > P_zetac:
+            KH3rdc = background
+        else:
+            if sigerr == 0:
+                KH3rdc = hval(Z3rdc, ifitx, ifity, ypk, sigk)
+            else:
+                KH3rdc, _ = linint(ifitx, ifity, Z3rdc)
+            if KH3rdc < background:
+                KH3rdc = background
+        r = 1.0
+        ParZc = ParZc + KprimeZc + dev[i - 1] * math.pow(2.0 / r * KH3rdc * deltat, 0.5)
+    return P_zc - ParZc, sigerr                                          # xi. :342
+
+
 # ---------------------------------------------------------------------- gridcell_module.f90
 def gridcell(ex, ey, X, Y):
     """gridcell_module.f90:26-257 for ONE element (checkele form): True <=> triangle /= 0"""

@@ -654,14 +654,16 @@ static void HTurb(ora_ctx* c, prng* g, double* TurbHx, double* TurbHy)
 }
 
 /* ---- VTurb (ver_turb_module.f90:30-380) ------------------------------------ */
-static double VTurb(ora_ctx* c, const elestate* es, prng* g, double P_zc, double P_depth, double P_zetac,
-    int p, const double ex[3], const double ix[3],
-    const double* Pwc_wzb, const double* Pwc_wzc, const double* Pwc_wzf)
+/* Everything of VTurb after step i. (the KH gather) and with the `loop` normal deviates of step ix.c handed in, so that
+ * it can be driven on a bare water column (ora_vturb_column, tests/test_oracle_differential.py).  trace_id: ORA_TRACE_ID. */
+static double VTurb_core(int ws, int idt, int p, const double ex[3], const double ix[3],
+    const double* KHb, const double* KHc, const double* KHf,
+    const double* Pwc_wzb, const double* Pwc_wzc, const double* Pwc_wzf,
+    double P_zc, double P_depth, double P_zetac, const double* dev, int* sigerr_out, long long trace_id)
 {
     const double background = F32(1.0E-6);                  /* ledger 2 */
-    int ws = c->prm.ws, p2 = ws * 4;
+    int p2 = ws * 4;
     size_t nb = sizeof(double) * (size_t)(p2 + 8);
-    double *KHb = malloc(nb), *KHc = malloc(nb), *KHf = malloc(nb);
     double *slb = malloc(nb), *slc = malloc(nb), *slf = malloc(nb), *icb = malloc(nb), *icc = malloc(nb), *icf = malloc(nb);
     double *mxb = malloc(nb), *myb = malloc(nb), *mxc = malloc(nb), *myc = malloc(nb), *mxf = malloc(nb), *myf = malloc(nb);
     double *fxb = malloc(nb), *fyb = malloc(nb), *fxc = malloc(nb), *fyc = malloc(nb), *fxf = malloc(nb), *fyf = malloc(nb);
@@ -669,12 +671,6 @@ static double VTurb(ora_ctx* c, const elestate* es, prng* g, double P_zc, double
     double *nxb = calloc(p2 + 8, 8), *nyb = calloc(p2 + 8, 8), *nxc = calloc(p2 + 8, 8), *nyc = calloc(p2 + 8, 8),
            *nxf = calloc(p2 + 8, 8), *nyf = calloc(p2 + 8, 8);
     double *YPK = malloc(nb), *SIGK = malloc(nb);
-    /* i. :102-108 */
-    for (int i = 1; i <= ws; ++i) {
-        KHb[i - 1] = getInterp_kh(c, es, c->t_b, i);
-        KHc[i - 1] = getInterp_kh(c, es, c->t_c, i);
-        KHf[i - 1] = getInterp_kh(c, es, c->t_f, i);
-    }
     /* ii.a :120-124 (arrays are 1-based in the comments, 0-based here) */
     for (int j = 1; j <= p2 + 7; ++j) {
         nxb[j - 1] = Pwc_wzb[0] + ((double)(float)(j - 4)) * (Pwc_wzb[ws - 1] - Pwc_wzb[0]) / (double)p2;
@@ -726,9 +722,9 @@ static double VTurb(ora_ctx* c, const elestate* es, prng* g, double P_zc, double
     }
     int IER, SigErr = 0;
     ora_tspsi(p2, fx, fy, YPK, SIGK, &IER, &SigErr);         /* :278-279 */
-    if (SigErr != 0) tl_nsig++;
+    *sigerr_out = SigErr;
     double deltat = 2.0;
-    int loop = c->prm.idt / (int)deltat;                     /* :283 */
+    int loop = idt / (int)deltat;                            /* :283 */
     double ParZc = P_zc;
     for (int i = 1; i <= loop; ++i) {                        /* :291-337 */
         double Kprimec = 0.0, thisyc, slopem;
@@ -744,19 +740,51 @@ static double VTurb(ora_ctx* c, const elestate* es, prng* g, double P_zc, double
             else ora_linint(fx, fy, p2, Z3rdc, &KH3rdc, &slopem);
             if (KH3rdc < background) KH3rdc = background;
         }
-        int q = i - 1;
-        double DEV = norm_(g, 1u + (uint32_t)(q >> 1), 2 * (q & 1));
+        double DEV = dev[i - 1];
         double r = 1.;
         ParZc = ParZc + KprimeZc + DEV * pow(2.0 / r * KH3rdc * deltat, 0.5);
-        if (getenv("ORA_TRACE_ID") && atoll(getenv("ORA_TRACE_ID")) == (long long)(((uint64_t)g->id_hi << 32) | g->id_lo))
+        if (trace_id >= 0 && getenv("ORA_TRACE_ID") && atoll(getenv("ORA_TRACE_ID")) == trace_id)
             fprintf(stderr, "ORATRACE %d %.17g %.17g %.17g %.17g\n", i - 1, ParZc, Kprimec, KH3rdc, DEV);
     }
     double TurbV = P_zc - ParZc;                             /* :342 (ledger 11) */
-    free(KHb); free(KHc); free(KHf); free(slb); free(slc); free(slf); free(icb); free(icc); free(icf);
+    free(slb); free(slc); free(slf); free(icb); free(icc); free(icf);
     free(mxb); free(myb); free(mxc); free(myc); free(mxf); free(myf);
     free(fxb); free(fyb); free(fxc); free(fyc); free(fxf); free(fyf); free(fx); free(fy);
     free(nxb); free(nyb); free(nxc); free(nyc); free(nxf); free(nyf); free(YPK); free(SIGK);
     return TurbV;
+}
+
+static double VTurb(ora_ctx* c, const elestate* es, prng* g, double P_zc, double P_depth, double P_zetac,
+    int p, const double ex[3], const double ix[3],
+    const double* Pwc_wzb, const double* Pwc_wzc, const double* Pwc_wzf)
+{
+    int ws = c->prm.ws, loop = c->prm.idt / 2;
+    double *KHb = malloc(sizeof(double) * (size_t)ws), *KHc = malloc(sizeof(double) * (size_t)ws), *KHf = malloc(sizeof(double) * (size_t)ws);
+    double* dev = malloc(sizeof(double) * (size_t)(loop > 0 ? loop : 1));
+    for (int i = 1; i <= ws; ++i) {                          /* i. :102-108 */
+        KHb[i - 1] = getInterp_kh(c, es, c->t_b, i);
+        KHc[i - 1] = getInterp_kh(c, es, c->t_c, i);
+        KHf[i - 1] = getInterp_kh(c, es, c->t_f, i);
+    }
+    /* the deviates of step ix.c in draw order (nothing else draws inside the loop) */
+    for (int q = 0; q < loop; ++q) dev[q] = norm_(g, 1u + (uint32_t)(q >> 1), 2 * (q & 1));
+    int SigErr = 0;
+    double TurbV = VTurb_core(ws, c->prm.idt, p, ex, ix, KHb, KHc, KHf, Pwc_wzb, Pwc_wzc, Pwc_wzf, P_zc, P_depth, P_zetac, dev, &SigErr,
+                              (long long)(((uint64_t)g->id_hi << 32) | g->id_lo));
+    if (SigErr != 0) tl_nsig++;
+    free(KHb); free(KHc); free(KHf); free(dev);
+    return TurbV;
+}
+
+/* VTurb on a bare column: KH and w-level depths at the three hydro times, `idt / 2` normal deviates. */
+double ora_vturb_column(int32_t ws, int32_t idt, int32_t p, const double ex[3], const double ix[3],
+    const double* KHb, const double* KHc, const double* KHf, const double* wzb, const double* wzc, const double* wzf,
+    double P_zc, double P_depth, double P_zetac, const double* dev, int32_t* sigerr)
+{
+    int se = 0;
+    double t = VTurb_core(ws, idt, p, ex, ix, KHb, KHc, KHf, wzb, wzc, wzf, P_zc, P_depth, P_zetac, dev, &se, -1);
+    *sigerr = se;
+    return t;
 }
 
 /* ---- behave (behavior_module.f90:181-551) ---------------------------------- */

@@ -250,3 +250,72 @@ def test_intersect_reflect_bit_equal_on_the_synthetic_coastline():
                 assert same(f[k].value, want[1 + k]), (it, k, f[k].value, want)
     assert hits > 1000
     o.destroy()
+
+
+# ---------------------------------------------------------------- VTurb on a bare column
+def _vturb_case(rng, ws, shared, p, loop, kmode):
+    """a water column the way update_particles hands it to VTurb: w-level depths and KH at the three hydro times"""
+    h = float(rng.uniform(4.0, 400.0))
+    frac = np.cumsum(rng.uniform(0.2, 3.0, ws - 1)); frac = np.concatenate([[0.0], frac / frac[-1]])
+    wz = []
+    for t in range(3):
+        zeta = float(rng.uniform(-0.6, 0.6))
+        f = frac if shared else np.concatenate([[0.0], np.cumsum(rng.uniform(0.2, 3.0, ws - 1))]); f = f / f[-1]
+        wz.append(-h + (h + zeta) * f)
+    z01 = np.linspace(0.0, 1.0, ws)
+    base = float(10.0 ** rng.uniform(-5.0, -1.5))
+    kh = []
+    for t in range(3):
+        if kmode == 0:      # smooth bump, zero at the bed and the surface like ROMS AKs
+            k = base * 4.0 * z01 * (1.0 - z01) * (1.0 + 0.3 * rng.standard_normal(ws)).clip(0.05, None)
+        elif kmode == 1:    # rough, with exact zeros: the time polynomial overshoots below 0 and the clamps bind
+            k = base * rng.uniform(0.0, 1.0, ws) * (rng.uniform(0, 1, ws) > 0.25)
+        else:               # nearly constant
+            k = base * (1.0 + 1e-3 * rng.standard_normal(ws))
+        kh.append(np.abs(k))
+    ex = np.array([0.0, 3600.0, 7200.0]) + 3600.0 * (p - 1)
+    it = int(rng.integers(0, 20)); idt = 2 * loop
+    ix = ex[1] + idt * np.array([it, it + 1.0, it + 2.0]) if p > 1 else ex[0] + idt * np.array([it, it + 1.0, it + 2.0])
+    zeta_c = float(wz[1][-1]); depth = float(wz[1][0])
+    P_zc = float(rng.uniform(depth, zeta_c))
+    dev = rng.standard_normal(loop)
+    return idt, ex, ix, kh, wz, P_zc, depth, zeta_c, dev
+
+
+@settings(max_examples=400, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(st.integers(0, 2 ** 31 - 1), st.integers(5, 24), st.booleans(), st.sampled_from([1, 2]), st.integers(3, 10), st.integers(0, 2))
+def test_vturb_column_bit_equal(seed, ws, shared, p, loop, kmode):
+    """ver_turb_module.f90:30-380 from the KH column to TurbV: resampling to 4 ws + 7 points with the walking jlo,
+    pads (KHb(1) below at all three times), 8-point moving average, time polynomial, clamps, (b + 4c + f)/6,
+    TSPSI on 4 ws knots, idt/2 random-displacement steps with HPVAL / HVAL or the linint fall-back: the C oracle's
+    VTurb and the Python restatement written from the Fortran give the same bits and the same SigErr verdict."""
+    rng = np.random.default_rng(seed)
+    idt, ex, ix, kh, wz, P_zc, depth, zeta_c, dev = _vturb_case(rng, ws, shared, p, loop, kmode)
+    se = C.c_int32(0)
+    got = L.ora_vturb_column(ws, idt, p, dptr(arr(ex)), dptr(arr(ix)), dptr(arr(kh[0])), dptr(arr(kh[1])), dptr(arr(kh[2])),
+                             dptr(arr(wz[0])), dptr(arr(wz[1])), dptr(arr(wz[2])), P_zc, depth, zeta_c, dptr(arr(dev)), C.byref(se))
+    want, sigerr = NL.vturb_column(ws, idt, p, list(ex), list(ix), list(kh[0]), list(kh[1]), list(kh[2]),
+                                   list(wz[0]), list(wz[1]), list(wz[2]), P_zc, depth, zeta_c, list(dev))
+    assert se.value == sigerr
+    assert same(got, want), (got, want, got - want)
+
+
+def test_vturb_column_takes_the_linint_branch_too():
+    """columns whose fit meets SigErr (a convexity interval with T in the failing band) walk on linint: searched for,
+    so that the fall-back branch of the loop is compared as well"""
+    found = 0
+    for seed in range(4000):
+        rng = np.random.default_rng(10_000 + seed)
+        idt, ex, ix, kh, wz, P_zc, depth, zeta_c, dev = _vturb_case(rng, 21, True, 2, 3, 0)
+        se = C.c_int32(0)
+        got = L.ora_vturb_column(21, idt, 2, dptr(arr(ex)), dptr(arr(ix)), dptr(arr(kh[0])), dptr(arr(kh[1])), dptr(arr(kh[2])),
+                                 dptr(arr(wz[0])), dptr(arr(wz[1])), dptr(arr(wz[2])), P_zc, depth, zeta_c, dptr(arr(dev)), C.byref(se))
+        if se.value == 0:
+            continue
+        want, sigerr = NL.vturb_column(21, idt, 2, list(ex), list(ix), list(kh[0]), list(kh[1]), list(kh[2]),
+                                       list(wz[0]), list(wz[1]), list(wz[2]), P_zc, depth, zeta_c, list(dev))
+        assert sigerr == se.value and same(got, want), (seed, got, want)
+        found += 1
+        if found >= 3:
+            break
+    assert found >= 1, "no SigErr column in the search range"
