@@ -353,6 +353,30 @@ def hpval(t, x, y, yp, sigma):
     return s + (tm * ((e2 - e1) * (d1 + d2) + tm * (d1 - d2)) + sig * ((e1 * ems - e2) * d1 + (e1 - e2 * ems) * d2)) / e
 
 
+# ------------------------------------------------------- hydrodynamic_module.f90 (WCTS_ITPI)
+def wcts_profile(zb, zc, zf, vb, vc, vf, P_zb, P_zc, P_zf, ex, ix, p, v):
+    """hydrodynamic_module.f90:2619-2689: the 4-knot tension spline of one field at the three hydro times (linint
+    when SIGS reports SigErr), then the time polynomial.  -> (value, SigErr fall-backs among the profiles used)"""
+    vals, nfall = [], 0
+    for k, (z, y, T) in enumerate(((zb, vb, P_zb), (zc, vc, P_zc), (zf, vf, P_zf))):
+        yp, sigm, ier, sigerr = tspsi(list(z), list(y))
+        if sigerr == 0:
+            vals.append(hval(T, list(z), list(y), yp, sigm))
+        else:
+            vals.append(linint(list(z), list(y), T)[0])
+            if not (k == 2 and p == 1):
+                nfall += 1
+    ey = [vals[0], vals[0], vals[1]] if p == 1 else [vals[0], vals[1], vals[2]]
+    b, c, f = polintd(ex, ey, ix[0]), polintd(ex, ey, ix[1]), polintd(ex, ey, ix[2])
+    if v == 1:
+        return b, nfall
+    if v == 2:
+        return c, nfall
+    if v == 3:
+        return f, nfall
+    return (b + c * 4 + f) / 6.0, nfall
+
+
 # --------------------------------------------------------------------- ver_turb_module.f90
 def _f32(v):
     """a single-precision literal as the double it widens to"""

@@ -561,6 +561,9 @@ static double interp(ora_ctx* c, const elestate* es, double xp, double yp, int f
 static __thread int tl_nsig;
 
 /* ---- WCTS_ITPI (hydro:2577-2689) ------------------------------------------ */
+static double WCTS_core(const double* abb_zb, const double* abb_zc, const double* abb_zf,
+    const double* abb_vb, const double* abb_vc, const double* abb_vf,
+    double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int v, int* nfall);
 static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, double Ypos, int deplvl,
     const double* Pwc_zb, const double* Pwc_zc, const double* Pwc_zf,
     double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int v)
@@ -575,17 +578,29 @@ static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, do
         abb_vc[i - 1] = interp(c, es, Xpos, Ypos, fld, c->t_c, i + deplvl - 1);
         abb_vf[i - 1] = interp(c, es, Xpos, Ypos, fld, c->t_f, i + deplvl - 1);
     }
+    int nfall = 0;
+    double r = WCTS_core(abb_zb, abb_zc, abb_zf, abb_vb, abb_vc, abb_vf, P_zb, P_zc, P_zf, ex, ix, p, v, &nfall);
+    tl_nsig += nfall;
+    return r;
+}
+
+/* WCTS_ITPI after the gather of the 4-level profiles (hydro:2619-2689); *nfall = SigErr fall-backs that count */
+static double WCTS_core(const double* abb_zb, const double* abb_zc, const double* abb_zf,
+    const double* abb_vb, const double* abb_vc, const double* abb_vf,
+    double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int v, int* nfall)
+{
+    enum { nN = 4 };
     double YP[nN], SIGM[nN], slope, P_vb = 0.0, P_vc = 0.0, P_vf = 0.0;
     int IER, SigErr;
     SigErr = 0; ora_tspsi(nN, abb_zb, abb_vb, YP, SIGM, &IER, &SigErr);
     if (SigErr == 0) P_vb = ora_hval(P_zb, nN, abb_zb, abb_vb, YP, SIGM, &IER);
-    else { ora_linint(abb_zb, abb_vb, nN, P_zb, &P_vb, &slope); tl_nsig++; }
+    else { ora_linint(abb_zb, abb_vb, nN, P_zb, &P_vb, &slope); (*nfall)++; }
     SigErr = 0; ora_tspsi(nN, abb_zc, abb_vc, YP, SIGM, &IER, &SigErr);
     if (SigErr == 0) P_vc = ora_hval(P_zc, nN, abb_zc, abb_vc, YP, SIGM, &IER);
-    else { ora_linint(abb_zc, abb_vc, nN, P_zc, &P_vc, &slope); tl_nsig++; }
+    else { ora_linint(abb_zc, abb_vc, nN, P_zc, &P_vc, &slope); (*nfall)++; }
     SigErr = 0; ora_tspsi(nN, abb_zf, abb_vf, YP, SIGM, &IER, &SigErr);
     if (SigErr == 0) P_vf = ora_hval(P_zf, nN, abb_zf, abb_vf, YP, SIGM, &IER);
-    else { ora_linint(abb_zf, abb_vf, nN, P_zf, &P_vf, &slope); if (p != 1) tl_nsig++; }   /* unused when p == 1 */
+    else { ora_linint(abb_zf, abb_vf, nN, P_zf, &P_vf, &slope); if (p != 1) (*nfall)++; }   /* unused when p == 1 */
     double ey[3];
     if (p == 1) { ey[0] = P_vb; ey[1] = P_vb; ey[2] = P_vc; }      /* ledger 8 */
     else        { ey[0] = P_vb; ey[1] = P_vc; ey[2] = P_vf; }
@@ -594,6 +609,16 @@ static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, do
     double vf = ora_polintd(ex, ey, ix[2]);
     double P_V = (vb + vc * 4 + vf) / 6.0;
     switch (v) { case 1: return vb; case 2: return vc; case 3: return vf; default: return P_V; }
+}
+
+/* WCTS_ITPI on bare 4-level profiles (tests/test_oracle_differential.py) */
+double ora_wcts_profile(const double* zb, const double* zc, const double* zf, const double* vb, const double* vc, const double* vf,
+    double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int32_t p, int32_t v, int32_t* nfall)
+{
+    int nf = 0;
+    double r = WCTS_core(zb, zc, zf, vb, vc, vf, P_zb, P_zc, P_zf, ex, ix, p, v, &nf);
+    *nfall = nf;
+    return r;
 }
 
 /* ---- find_currents (LTRANS.f90:1422-1614) --------------------------------- */

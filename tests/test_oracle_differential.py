@@ -319,3 +319,71 @@ def test_vturb_column_takes_the_linint_branch_too():
         if found >= 3:
             break
     assert found >= 1, "no SigErr column in the search range"
+
+
+# ---------------------------------------------------------------- WCTS_ITPI on bare 4-level profiles
+def _wcts_case(rng, p):
+    z, v = [], []
+    z0 = float(rng.uniform(-300.0, -2.0))
+    for t in range(3):
+        dz = rng.uniform(0.05, 20.0, 3)
+        z.append(z0 + float(rng.uniform(-0.3, 0.3)) + np.concatenate([[0.0], np.cumsum(dz)]))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            v.append(rng.uniform(-1.5, 1.5, 4))                                  # rough: velocities
+        elif kind == 1:
+            v.append(np.sort(rng.uniform(0.0, 35.0, 4)))                          # monotone: salinity-like
+        else:
+            v.append(float(rng.uniform(-1, 1)) + 1e-3 * rng.standard_normal(4))  # nearly flat
+    P = [float(rng.uniform(z[t][0] - 0.5, z[t][3] + 0.5)) for t in range(3)]      # also just outside the window
+    ex = np.array([0.0, 3600.0, 7200.0]) + 3600.0 * (p - 1)
+    it = int(rng.integers(0, 28))
+    ix = (ex[1] if p > 1 else ex[0]) + 120.0 * np.array([it, it + 1.0, it + 2.0])
+    return z, v, P, ex, ix
+
+
+def _wcts_both(z, v, P, ex, ix, p, ver):
+    nf = C.c_int32(0)
+    got = L.ora_wcts_profile(dptr(arr(z[0])), dptr(arr(z[1])), dptr(arr(z[2])), dptr(arr(v[0])), dptr(arr(v[1])), dptr(arr(v[2])),
+                             P[0], P[1], P[2], dptr(arr(ex)), dptr(arr(ix)), p, ver, C.byref(nf))
+    return got, nf.value
+
+
+@settings(max_examples=1500, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(st.integers(0, 2 ** 31 - 1), st.sampled_from([1, 2]), st.integers(1, 4))
+def test_wcts_itpi_profile_bit_equal(seed, p, ver):
+    """hydrodynamic_module.f90:2619-2689: TSPSI + HVAL on the 4 levels around the particle at the three hydro times
+    (or linint after SigErr), the p == 1 triplet (b, b, c), polintd to the internal times, versions 1-4"""
+    z, v, P, ex, ix = _wcts_case(np.random.default_rng(seed), p)
+    got, nf = _wcts_both(z, v, P, ex, ix, p, ver)
+    want, nfall = NL.wcts_profile(list(z[0]), list(z[1]), list(z[2]), list(v[0]), list(v[1]), list(v[2]), P[0], P[1], P[2], list(ex), list(ix), p, ver)
+    assert nf == nfall and same(got, want), (got, want)
+
+
+# 4-level profiles that meet SigErr (found by a search over 400 000 random cases of _wcts_case: 3 hits), as hex floats
+_WCTS_SIGERR = [
+    ([['-0x1.43ba699d91bb2p+5', '-0x1.35026af9b1bcap+5', '-0x1.266e47a46f4e4p+5', '-0x1.6dfce01700e38p+4'], ['-0x1.440ea1156449ap+5', '-0x1.1b83fc27c94e9p+5', '-0x1.12c7a4c899206p+5', '-0x1.03bc04c87404bp+4'], ['-0x1.45d56f72e4940p+5', '-0x1.d4905dfcd0746p+4', '-0x1.50bddfcf46a40p+3', '0x1.9f8213dd13340p+2']],
+     [['-0x1.20ae68af14889p-1', '0x1.f40ad80ca2230p-2', '0x1.480681fc08548p+0', '0x1.0bccbc49e2dcep+0'], ['0x1.0f083adde7555p-1', '0x1.10e7d6c9d207dp-1', '0x1.0fef3c7408c6dp-1', '0x1.10093c741d348p-1'], ['0x1.8702b57ca1a27p-4', '0x1.8c738b4d8aa1ep-4', '0x1.8c92e05d93785p-4', '0x1.92dd96af245ccp-4']],
+     ['-0x1.33b7d8acc5889p+5', '-0x1.4665f887805c5p+5', '-0x1.3686479bbb758p+3'], [3600.0, 7200.0, 10800.0], [7200.0, 7320.0, 7440.0]),
+    ([['-0x1.e784c92d84a90p+7', '-0x1.c48fee03f82eep+7', '-0x1.a916e1695cc0cp+7', '-0x1.8b11ca12e7543p+7'], ['-0x1.e7539da9f1985p+7', '-0x1.d6221dd30bc5ap+7', '-0x1.b9563cb6d171cp+7', '-0x1.acf418237eb96p+7'], ['-0x1.e7be65570f77bp+7', '-0x1.c19390003e5bep+7', '-0x1.a449259dbcc86p+7', '-0x1.8c13097e9233bp+7']],
+     [['0x1.ceb53eada41bep+2', '0x1.11987124effaep+3', '0x1.25cbcd3f45ab5p+3', '0x1.d0902a6bf6988p+3'], ['0x1.a8301aeb0abedp+2', '0x1.b07a85d8dea3bp+3', '0x1.fbd1ba76e452dp+3', '0x1.02ea8de8cbb6bp+5'], ['-0x1.e4a569815b282p-3', '-0x1.e6f393701bc5fp-3', '-0x1.e7e9b55948123p-3', '-0x1.e7a25650ac188p-3']],
+     ['-0x1.e4d1e4ddbe14ep+7', '-0x1.cc059c13ecc80p+7', '-0x1.98b0e7ba0f014p+7'], [3600.0, 7200.0, 10800.0], [10440.0, 10560.0, 10680.0]),
+    ([['-0x1.2d851194d74f4p+7', '-0x1.2338eae3aa40ap+7', '-0x1.0802a31d099c5p+7', '-0x1.e24f7985a7b1ap+6'], ['-0x1.2d830c6f2db88p+7', '-0x1.2c7f5c81bae8fp+7', '-0x1.21f8d8f65d202p+7', '-0x1.17af17274a499p+7'], ['-0x1.2daca089b96edp+7', '-0x1.236cb399b3cb3p+7', '-0x1.0cb3e3ab7ef84p+7', '-0x1.f0faa76f1f752p+6']],
+     [['0x1.32f7a4dc98b71p-3', '0x1.3322c07b23c4dp-3', '0x1.3423148d9a61dp-3', '0x1.3155827740e09p-3'], ['0x1.315c7857efb48p-2', '0x1.c4ecae0d62e60p-2', '-0x1.2c0c56b956bc2p+0', '-0x1.c43b751ae3cd8p-2'], ['0x1.e6e48efb081ffp+2', '0x1.2ab233270cb4dp+3', '0x1.39ac168cb6549p+3', '0x1.c23bc4d4e5371p+4']],
+     ['-0x1.199777093879dp+7', '-0x1.1ab512934e571p+7', '-0x1.29742c6f1c273p+7'], [3600.0, 7200.0, 10800.0], [9600.0, 9720.0, 9840.0]),
+]
+
+
+def test_wcts_itpi_profile_linint_branch():
+    """profiles that meet SigErr take linint on both sides, for every version and both triplets"""
+    H = float.fromhex
+    for z, v, P, ex, ix in _WCTS_SIGERR:
+        z = [np.array([H(x) for x in a]) for a in z]; v = [np.array([H(x) for x in a]) for a in v]; P = [H(x) for x in P]
+        hit = 0
+        for p in (1, 2):
+            for ver in (1, 2, 3, 4):
+                got, nf = _wcts_both(z, v, P, np.array(ex), np.array(ix), p, ver)
+                want, nfall = NL.wcts_profile(list(z[0]), list(z[1]), list(z[2]), list(v[0]), list(v[1]), list(v[2]), P[0], P[1], P[2], list(ex), list(ix), p, ver)
+                assert nf == nfall and same(got, want), (p, ver, got, want)
+                hit += nf
+        assert hit > 0
