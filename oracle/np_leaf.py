@@ -353,6 +353,62 @@ def hpval(t, x, y, yp, sigma):
     return s + (tm * ((e2 - e1) * (d1 + d2) + tm * (d1 - d2)) + sig * ((e1 * ems - e2) * d1 + (e1 - e2 * ems) * d2)) / e
 
 
+# ------------------------------------------- hydrodynamic_module.f90 (setInterp / getInterp / interp)
+def _tri(xp, yp, xa, ya, xb, yb, xc, yc):
+    """barycentric pair of (xp, yp) in the triangle with origin a and edges to b (t) and c (u), hydro:1706-1707"""
+    t = ((xp - xa) * (yc - ya) + (ya - yp) * (xc - xa)) / ((xb - xa) * (yc - ya) - (yb - ya) * (xc - xa))
+    u = ((xp - xa) * (yb - ya) + (ya - yp) * (xb - xa)) / ((xc - xa) * (yb - ya) - (yc - ya) * (xb - xa))
+    return t, u
+
+
+def _idw(x, y, xp, yp):
+    dis = [1.0 / math.sqrt((x[i] - xp) ** 2 + (y[i] - yp) ** 2) for i in range(4)]
+    td = dis[0] + dis[1] + dis[2] + dis[3]
+    return [dis[0] / td, dis[1] / td, dis[2] / td, dis[3] / td]
+
+
+def set_get_interp(x, y, v, xp, yp):
+    """setInterp (hydro:1680-1740) then getInterp's combination (:1996-2004).  Note the reference's quirk: a point
+    ON a node that lies outside both triangles' (t, u) tests gets Wgt = 1 for that node but tOK stays 2, so
+    getInterp still combines with the second triangle's t and u."""
+    wgt = [0.0, 0.0, 0.0, 0.0]
+    t, u = _tri(xp, yp, x[0], y[0], x[1], y[1], x[2], y[2]); tok = 1
+    if t < 0.0 or u < 0.0 or (t + u) > 1.0:
+        t, u = _tri(xp, yp, x[2], y[2], x[3], y[3], x[0], y[0]); tok = 2
+        if t < 0.0 or u < 0.0 or (t + u) > 1.0:
+            on = [xp == x[i] and yp == y[i] for i in range(4)]
+            if any(on):
+                for i in range(4):
+                    if on[i]:
+                        wgt[i] = 1.0
+            else:
+                wgt = _idw(x, y, xp, yp); tok = 3
+    if tok == 1:
+        return v[0] + (v[1] - v[0]) * t + (v[2] - v[0]) * u
+    if tok == 2:
+        return v[2] + (v[3] - v[2]) * t + (v[0] - v[2]) * u
+    return wgt[0] * v[0] + wgt[1] * v[1] + wgt[2] * v[2] + wgt[3] * v[3]
+
+
+def interp_quad(x, y, v, xp, yp):
+    """interp (hydro:2533-2565): the same three methods with the weights worked out per call; on a node: its value"""
+    tt, uu = _tri(xp, yp, x[0], y[0], x[1], y[1], x[2], y[2])
+    vp = v[0] + (v[1] - v[0]) * tt + (v[2] - v[0]) * uu
+    if tt < 0.0 or uu < 0.0 or (tt + uu) > 1.0:
+        tt, uu = _tri(xp, yp, x[2], y[2], x[3], y[3], x[0], y[0])
+        vp = v[2] + (v[3] - v[2]) * tt + (v[0] - v[2]) * uu
+        if tt < 0.0 or uu < 0.0 or (tt + uu) > 1.0:
+            on = [xp == x[i] and yp == y[i] for i in range(4)]
+            if any(on):
+                for i in range(4):
+                    if on[i]:
+                        vp = v[i]
+            else:
+                w = _idw(x, y, xp, yp)
+                vp = w[0] * v[0] + w[1] * v[1] + w[2] * v[2] + w[3] * v[3]
+    return vp
+
+
 # ------------------------------------------------------- hydrodynamic_module.f90 (WCTS_ITPI)
 def wcts_profile(zb, zc, zf, vb, vc, vf, P_zb, P_zc, P_zf, ex, ix, p, v):
     """hydrodynamic_module.f90:2619-2689: the 4-knot tension spline of one field at the three hydro times (linint

@@ -556,6 +556,22 @@ static double interp(ora_ctx* c, const elestate* es, double xp, double yp, int f
     return vp;
 }
 
+/* The two horizontal interpolators on a bare quadrilateral (tests/test_oracle_differential.py): corner coordinates
+ * x[4], y[4] and corner values v[4] in the element's node order.  which = 0: setInterp + getInterp (hydro:1680-1740,
+ * 1996-2004: weights stored once, an on-node point outside both triangles keeps tOK = 2); 1: interp (hydro:2533-2565:
+ * weights per call, an on-node point takes the node value).  Built on the same routines the step uses. */
+double ora_interp_quad(const double x[4], const double y[4], const double v[4], double xp, double yp, int32_t which)
+{
+    ora_ctx c; memset(&c, 0, sizeof c);
+    elestate es; memset(&es, 0, sizeof es);
+    double rx[4] = {x[0], x[1], x[2], x[3]}, ry[4] = {y[0], y[1], y[2], y[3]};
+    double fld[12];
+    for (int i = 0; i < 4; ++i) { es.rnode[i] = i + 1; fld[3 * i] = fld[3 * i + 1] = fld[3 * i + 2] = v[i]; }
+    c.rx = rx; c.ry = ry; c.rho_nodes = 4; c.t_Wvel = fld;
+    if (which == 0) { setInterp(&c, &es, xp, yp); return combine(&es, v); }
+    return interp(&c, &es, xp, yp, FLD_W, 1, 1);
+}
+
 /* diagnostic only: SigErr (linint) fall-backs that reached a result during the current
  * particle-step; summed per particle for ora_fetch_sigerr */
 static __thread int tl_nsig;

@@ -387,3 +387,40 @@ def test_wcts_itpi_profile_linint_branch():
                 assert nf == nfall and same(got, want), (p, ver, got, want)
                 hit += nf
         assert hit > 0
+
+
+# ---------------------------------------------------------------- setInterp / getInterp / interp on a bare quadrilateral
+def _quad(rng):
+    """a ROMS-like cell: a jittered rectangle in metres, node order as hydro:416-519 (counter-clockwise from the lower left)"""
+    x0, y0 = rng.uniform(-5e5, 5e5), rng.uniform(-5e5, 5e5)
+    dx, dy = rng.uniform(200.0, 8000.0), rng.uniform(200.0, 8000.0)
+    j = rng.uniform(-0.15, 0.15, (4, 2))
+    x = np.array([x0 + j[0, 0] * dx, x0 + dx + j[1, 0] * dx, x0 + dx + j[2, 0] * dx, x0 + j[3, 0] * dx])
+    y = np.array([y0 + j[0, 1] * dy, y0 + j[1, 1] * dy, y0 + dy + j[2, 1] * dy, y0 + dy + j[3, 1] * dy])
+    return x, y, rng.uniform(-3.0, 3.0, 4)
+
+
+@settings(max_examples=3000, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(st.integers(0, 2 ** 31 - 1), st.integers(0, 1), st.integers(0, 4))
+def test_interp_quad_bit_equal(seed, which, where):
+    """first triangle, second triangle, inverse-distance fall-back (points outside the cell), points ON nodes and on
+    the shared diagonal: setInterp + getInterp (with its on-node quirk) and interp, bit for bit"""
+    rng = np.random.default_rng(seed)
+    x, y, v = _quad(rng)
+    if where == 0:                                   # anywhere in and around the cell
+        a, b = rng.uniform(-0.4, 1.4, 2)
+        xp = x[0] + a * (x[1] - x[0]) + b * (x[3] - x[0]); yp = y[0] + a * (y[1] - y[0]) + b * (y[3] - y[0])
+    elif where == 1:                                 # on a node
+        k = int(rng.integers(0, 4)); xp, yp = x[k], y[k]
+    elif where == 2:                                 # on the diagonal 1-3 shared by the two triangles
+        a = rng.uniform(0.0, 1.0); xp = x[0] + a * (x[2] - x[0]); yp = y[0] + a * (y[2] - y[0])
+    elif where == 3:                                 # on an edge
+        k = int(rng.integers(0, 4)); a = rng.uniform(0.0, 1.0)
+        xp = x[k] + a * (x[(k + 1) % 4] - x[k]); yp = y[k] + a * (y[(k + 1) % 4] - y[k])
+    else:                                            # well outside: inverse distance
+        xp = x[0] - rng.uniform(0.1, 3.0) * abs(x[1] - x[0]); yp = y[0] - rng.uniform(0.1, 3.0) * abs(y[3] - y[0])
+    got = L.ora_interp_quad(dptr(arr(x)), dptr(arr(y)), dptr(arr(v)), float(xp), float(yp), which)
+    f = NL.set_get_interp if which == 0 else NL.interp_quad
+    with np.errstate(all="ignore"):
+        want = f([float(a) for a in x], [float(a) for a in y], [float(a) for a in v], float(xp), float(yp))
+    assert same(got, want), (which, where, got, want)
