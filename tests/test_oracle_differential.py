@@ -390,7 +390,7 @@ def test_wcts_itpi_profile_linint_branch():
 
 
 # ---------------------------------------------------------------- setInterp / getInterp / interp on a bare quadrilateral
-def _quad(rng):
+def _cell(rng):
     """a ROMS-like cell: a jittered rectangle in metres, node order as hydro:416-519 (counter-clockwise from the lower left)"""
     x0, y0 = rng.uniform(-5e5, 5e5), rng.uniform(-5e5, 5e5)
     dx, dy = rng.uniform(200.0, 8000.0), rng.uniform(200.0, 8000.0)
@@ -406,7 +406,7 @@ def test_interp_quad_bit_equal(seed, which, where):
     """first triangle, second triangle, inverse-distance fall-back (points outside the cell), points ON nodes and on
     the shared diagonal: setInterp + getInterp (with its on-node quirk) and interp, bit for bit"""
     rng = np.random.default_rng(seed)
-    x, y, v = _quad(rng)
+    x, y, v = _cell(rng)
     if where == 0:                                   # anywhere in and around the cell
         a, b = rng.uniform(-0.4, 1.4, 2)
         xp = x[0] + a * (x[1] - x[0]) + b * (x[3] - x[0]); yp = y[0] + a * (y[1] - y[0]) + b * (y[3] - y[0])
