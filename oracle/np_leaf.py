@@ -362,7 +362,7 @@ def _tri(xp, yp, xa, ya, xb, yb, xc, yc):
 
 
 def _idw(x, y, xp, yp):
-    dis = [1.0 / math.sqrt((x[i] - xp) ** 2 + (y[i] - yp) ** 2) for i in range(4)]
+    dis = [1.0 / math.sqrt((x[i] - xp) * (x[i] - xp) + (y[i] - yp) * (y[i] - yp)) for i in range(4)]   # **2 is a product in Fortran
     td = dis[0] + dis[1] + dis[2] + dis[3]
     return [dis[0] / td, dis[1] / td, dis[2] / td, dis[3] / td]
 
@@ -784,7 +784,7 @@ def create_poly_specs_literal(r_ele_x, r_ele_y, polys, maxbdis):
                 lst.append(q)
                 continue
             if j == pedges - 1 or polys[j][0] != polys[j + 1][0]:
-                near = any(math.sqrt((ex[k] - polys[j][1]) ** 2 + (ey[k] - polys[j][2]) ** 2) < maxbdis[q] for k in range(4))
+                near = any(math.sqrt(_sq(ex[k] - polys[j][1]) + _sq(ey[k] - polys[j][2])) < maxbdis[q] for k in range(4))
                 if near:
                     pts = [(polys[first[q] + k][3], polys[first[q] + k][4]) for k in range(count[q])]
                     if any(inpoly(ex[k], ey[k], pts) for k in range(4)):
