@@ -433,6 +433,50 @@ def wcts_profile(zb, zc, zf, vb, vc, vf, P_zb, P_zc, P_zf, ex, ix, p, v):
     return (b + c * 4 + f) / 6.0, nfall
 
 
+# ------------------------------------------------------------------ LTRANS.f90 (find_currents)
+def find_currents_column(us, ws, z0, Zpar, z, wz, u, v, w, P_zb, P_zc, P_zf, ex, ix, p, version):
+    """LTRANS.f90:1422-1614 on a bare column.  z[t][k], wz[t][k]: rho- / w-level depths (t = 0, 1, 2 = back, centre,
+    forward; k 0-based), u, v (us levels) and w (ws levels) the field values at the particle.
+    -> (Uad, Vad, Wad, SigErr fall-backs)"""
+    Z = lambda t, i: z[t][i - 1]          # 1-based level access like the Fortran
+    WZ = lambda t, i: wz[t][i - 1]
+    # lowest numbered level of the closest four, :1450-1467 (the DO variable is us - 1 / ws - 1 after a complete loop)
+    i = 3
+    while i <= us - 2:
+        if Zpar < Z(0, i) or Zpar < Z(1, i) or Zpar < Z(2, i):
+            break
+        i += 1
+    ii = i - 2
+    i = 3
+    while i <= ws - 2:
+        if Zpar < WZ(0, i) or Zpar < WZ(1, i) or Zpar < WZ(2, i):
+            break
+        i += 1
+    iii = i - 2
+    nfall = 0
+    if Zpar < WZ(0, 1) + z0 or Zpar < WZ(1, 1) + z0 or Zpar < WZ(2, 1) + z0:               # :1480-1486
+        return 0.0, 0.0, 0.0, 0
+    if Zpar < Z(0, 1) or Zpar < Z(1, 1) or Zpar < Z(2, 1):                                   # log layer :1489-1600
+        num = lambda: math.log10((Zpar - WZ(0, 1)) / z0)
+        out = []
+        for fld, lev, top in ((u, 1, None), (v, 1, None), (w, 2, "w")):
+            vals = []
+            for t in range(3):
+                # note: the reference measures every height from the BACK record's bed, Pwc_wzb(1)
+                ref = (WZ(t, 2) if top == "w" else Z(t, 1)) - WZ(0, 1)
+                vals.append(fld[t][lev - 1] * num() / math.log10(ref / z0))
+            ey = [vals[0], vals[0], vals[1]] if p == 1 else vals
+            out.append(polintd(ex, ey, ix[version - 1]))
+        return out[0], out[1], out[2], 0
+    res = []
+    for fld, lvl, zz in ((u, ii, z), (v, ii, z), (w, iii, wz)):
+        prof = [[fld[t][lvl - 1 + k] for k in range(4)] for t in range(3)]
+        zs = [[zz[t][lvl - 1 + k] for k in range(4)] for t in range(3)]
+        val, nf = wcts_profile(zs[0], zs[1], zs[2], prof[0], prof[1], prof[2], P_zb, P_zc, P_zf, ex, ix, p, version)
+        res.append(val); nfall += nf
+    return res[0], res[1], res[2], nfall
+
+
 # --------------------------------------------------------------------- ver_turb_module.f90
 def _f32(v):
     """a single-precision literal as the double it widens to"""

@@ -580,7 +580,17 @@ static __thread int tl_nsig;
 static double WCTS_core(const double* abb_zb, const double* abb_zc, const double* abb_zf,
     const double* abb_vb, const double* abb_vc, const double* abb_vf,
     double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int v, int* nfall);
-static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, double Ypos, int deplvl,
+/* Where find_currents / WCTS_ITPI get a field value at the particle: in the step, interp() at (Xpos, Ypos) in the
+ * elements of the last setEle; in ora_find_currents_column, bare profiles handed in by the test. when = 0, 1, 2: the
+ * back, centre, forward hydro record; lev 1-based. */
+typedef double (*valfn)(const void* h, int fld, int when, int lev);
+typedef struct { ora_ctx* c; const elestate* es; double X, Y; } stepvals;
+static double stepvals_get(const void* h, int fld, int when, int lev)
+{
+    const stepvals* s = (const stepvals*)h;
+    return interp(s->c, s->es, s->X, s->Y, fld, when == 0 ? s->c->t_b : when == 1 ? s->c->t_c : s->c->t_f, lev);
+}
+static double WCTS_get(valfn get, const void* h, int fld, int deplvl,
     const double* Pwc_zb, const double* Pwc_zc, const double* Pwc_zf,
     double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int v)
 {
@@ -590,14 +600,21 @@ static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, do
         abb_zb[i - 1] = Pwc_zb[i + deplvl - 2];
         abb_zc[i - 1] = Pwc_zc[i + deplvl - 2];
         abb_zf[i - 1] = Pwc_zf[i + deplvl - 2];
-        abb_vb[i - 1] = interp(c, es, Xpos, Ypos, fld, c->t_b, i + deplvl - 1);
-        abb_vc[i - 1] = interp(c, es, Xpos, Ypos, fld, c->t_c, i + deplvl - 1);
-        abb_vf[i - 1] = interp(c, es, Xpos, Ypos, fld, c->t_f, i + deplvl - 1);
+        abb_vb[i - 1] = get(h, fld, 0, i + deplvl - 1);
+        abb_vc[i - 1] = get(h, fld, 1, i + deplvl - 1);
+        abb_vf[i - 1] = get(h, fld, 2, i + deplvl - 1);
     }
     int nfall = 0;
     double r = WCTS_core(abb_zb, abb_zc, abb_zf, abb_vb, abb_vc, abb_vf, P_zb, P_zc, P_zf, ex, ix, p, v, &nfall);
     tl_nsig += nfall;
     return r;
+}
+static double WCTS_ITPI(ora_ctx* c, const elestate* es, int fld, double Xpos, double Ypos, int deplvl,
+    const double* Pwc_zb, const double* Pwc_zc, const double* Pwc_zf,
+    double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int v)
+{
+    stepvals sv = { c, es, Xpos, Ypos };
+    return WCTS_get(stepvals_get, &sv, fld, deplvl, Pwc_zb, Pwc_zc, Pwc_zf, P_zb, P_zc, P_zf, ex, ix, p, v);
 }
 
 /* WCTS_ITPI after the gather of the 4-level profiles (hydro:2619-2689); *nfall = SigErr fall-backs that count */
@@ -638,13 +655,12 @@ double ora_wcts_profile(const double* zb, const double* zc, const double* zf, co
 }
 
 /* ---- find_currents (LTRANS.f90:1422-1614) --------------------------------- */
-static void find_currents(ora_ctx* c, const elestate* es, double Xpar, double Ypar, double Zpar,
+static void find_currents_core(int us, int ws, double z0, valfn get, const void* h, double Zpar,
     const double* Pwc_zb, const double* Pwc_zc, const double* Pwc_zf,
     const double* Pwc_wzb, const double* Pwc_wzc, const double* Pwc_wzf,
     double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int version,
     double* Uad, double* Vad, double* Wad)
 {
-    int us = c->prm.us, ws = c->prm.ws; double z0 = c->prm.z0;
     int i;
     for (i = 3; i <= us - 2; ++i)
         if (Zpar < Pwc_zb[i - 1] || Zpar < Pwc_zc[i - 1] || Zpar < Pwc_zf[i - 1]) break;
@@ -655,12 +671,9 @@ static void find_currents(ora_ctx* c, const elestate* es, double Xpar, double Yp
     if (Zpar < Pwc_wzb[0] + z0 || Zpar < Pwc_wzc[0] + z0 || Zpar < Pwc_wzf[0] + z0) {
         *Uad = 0.0; *Vad = 0.0; *Wad = 0.0;
     } else if (Zpar < Pwc_zb[0] || Zpar < Pwc_zc[0] || Zpar < Pwc_zf[0]) {
-        double Ub = interp(c, es, Xpar, Ypar, FLD_U, c->t_b, 1), Uc = interp(c, es, Xpar, Ypar, FLD_U, c->t_c, 1),
-               Uf = interp(c, es, Xpar, Ypar, FLD_U, c->t_f, 1);
-        double Vb = interp(c, es, Xpar, Ypar, FLD_V, c->t_b, 1), Vc = interp(c, es, Xpar, Ypar, FLD_V, c->t_c, 1),
-               Vf = interp(c, es, Xpar, Ypar, FLD_V, c->t_f, 1);
-        double Wb = interp(c, es, Xpar, Ypar, FLD_W, c->t_b, 2), Wc = interp(c, es, Xpar, Ypar, FLD_W, c->t_c, 2),
-               Wf = interp(c, es, Xpar, Ypar, FLD_W, c->t_f, 2);
+        double Ub = get(h, FLD_U, 0, 1), Uc = get(h, FLD_U, 1, 1), Uf = get(h, FLD_U, 2, 1);
+        double Vb = get(h, FLD_V, 0, 1), Vc = get(h, FLD_V, 1, 1), Vf = get(h, FLD_V, 2, 1);
+        double Wb = get(h, FLD_W, 0, 2), Wc = get(h, FLD_W, 1, 2), Wf = get(h, FLD_W, 2, 2);
         /* :1512 `stop 'dividing by 0'` when z0 == 0: caller guarantees z0 != 0 (checked at create) */
         double P_Ub = Ub * log10((Zpar - Pwc_wzb[0]) / z0) / log10((Pwc_zb[0] - Pwc_wzb[0]) / z0);
         double P_Uc = Uc * log10((Zpar - Pwc_wzb[0]) / z0) / log10((Pwc_zc[0] - Pwc_wzb[0]) / z0);
@@ -679,10 +692,41 @@ static void find_currents(ora_ctx* c, const elestate* es, double Xpar, double Yp
         if (p == 1) { ey[0] = P_Wb; ey[1] = P_Wb; ey[2] = P_Wc; } else { ey[0] = P_Wb; ey[1] = P_Wc; ey[2] = P_Wf; }
         *Wad = ora_polintd(ex, ey, xt);
     } else {
-        *Uad = WCTS_ITPI(c, es, FLD_U, Xpar, Ypar, ii, Pwc_zb, Pwc_zc, Pwc_zf, P_zb, P_zc, P_zf, ex, ix, p, version);
-        *Vad = WCTS_ITPI(c, es, FLD_V, Xpar, Ypar, ii, Pwc_zb, Pwc_zc, Pwc_zf, P_zb, P_zc, P_zf, ex, ix, p, version);
-        *Wad = WCTS_ITPI(c, es, FLD_W, Xpar, Ypar, iii, Pwc_wzb, Pwc_wzc, Pwc_wzf, P_zb, P_zc, P_zf, ex, ix, p, version);
+        *Uad = WCTS_get(get, h, FLD_U, ii, Pwc_zb, Pwc_zc, Pwc_zf, P_zb, P_zc, P_zf, ex, ix, p, version);
+        *Vad = WCTS_get(get, h, FLD_V, ii, Pwc_zb, Pwc_zc, Pwc_zf, P_zb, P_zc, P_zf, ex, ix, p, version);
+        *Wad = WCTS_get(get, h, FLD_W, iii, Pwc_wzb, Pwc_wzc, Pwc_wzf, P_zb, P_zc, P_zf, ex, ix, p, version);
     }
+}
+static void find_currents(ora_ctx* c, const elestate* es, double Xpar, double Ypar, double Zpar,
+    const double* Pwc_zb, const double* Pwc_zc, const double* Pwc_zf,
+    const double* Pwc_wzb, const double* Pwc_wzc, const double* Pwc_wzf,
+    double P_zb, double P_zc, double P_zf, const double ex[3], const double ix[3], int p, int version,
+    double* Uad, double* Vad, double* Wad)
+{
+    stepvals sv = { c, es, Xpar, Ypar };
+    find_currents_core(c->prm.us, c->prm.ws, c->prm.z0, stepvals_get, &sv, Zpar, Pwc_zb, Pwc_zc, Pwc_zf, Pwc_wzb, Pwc_wzc, Pwc_wzf,
+                       P_zb, P_zc, P_zf, ex, ix, p, version, Uad, Vad, Wad);
+}
+
+/* find_currents (LTRANS.f90:1422-1614) on a bare water column: rho- and w-level depths z[3][us], wz[3][ws] and the
+ * u, v (us levels) and w (ws levels) profiles at the particle, each [3 records][levels]; *nfall = SigErr fall-backs */
+typedef struct { const double *u, *v, *w; int us, ws; } colvals;
+static double colvals_get(const void* h, int fld, int when, int lev)
+{
+    const colvals* q = (const colvals*)h;
+    if (fld == FLD_U) return q->u[when * q->us + lev - 1];
+    if (fld == FLD_V) return q->v[when * q->us + lev - 1];
+    return q->w[when * q->ws + lev - 1];
+}
+void ora_find_currents_column(int32_t us, int32_t ws, double z0, double Zpar, const double* z, const double* wz,
+    const double* u, const double* v, const double* w, double P_zb, double P_zc, double P_zf,
+    const double ex[3], const double ix[3], int32_t p, int32_t version, double out[3], int32_t* nfall)
+{
+    colvals q = { u, v, w, us, ws };
+    int before = tl_nsig;
+    find_currents_core(us, ws, z0, colvals_get, &q, Zpar, z, z + us, z + 2 * us, wz, wz + ws, wz + 2 * ws,
+                       P_zb, P_zc, P_zf, ex, ix, p, version, &out[0], &out[1], &out[2]);
+    *nfall = tl_nsig - before; tl_nsig = before;
 }
 
 /* ---- HTurb (hor_turb_module.f90:29-50) ------------------------------------- */

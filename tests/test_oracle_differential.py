@@ -424,3 +424,44 @@ def test_interp_quad_bit_equal(seed, which, where):
     with np.errstate(all="ignore"):
         want = f([float(a) for a in x], [float(a) for a in y], [float(a) for a in v], float(xp), float(yp))
     assert same(got, want), (which, where, got, want)
+
+
+# ---------------------------------------------------------------- find_currents on a bare column
+@settings(max_examples=1200, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(st.integers(0, 2 ** 31 - 1), st.integers(6, 30), st.sampled_from([1, 2]), st.integers(1, 3), st.integers(0, 3))
+def test_find_currents_column_bit_equal(seed, us, p, version, where):
+    """LTRANS.f90:1422-1614: the level-window search, the three regimes (within z0 of the bed: zero; below the lowest
+    rho level: log layer measured from the back record's bed; else WCTS_ITPI on the four closest levels of the rho
+    grid for u, v and of the w grid for w), the p == 1 triplet and the version -> internal time choice"""
+    rng = np.random.default_rng(seed)
+    ws = us + 1
+    h = float(rng.uniform(3.0, 500.0)); z0 = float(rng.choice([0.001, 0.01, 0.05]))
+    frac = np.concatenate([[0.0], np.cumsum(rng.uniform(0.3, 2.0, ws - 1))]); frac = frac / frac[-1]
+    wz, z = [], []
+    for t in range(3):
+        zeta = float(rng.uniform(-0.5, 0.5))
+        lev = -h + (h + zeta) * frac
+        wz.append(lev); z.append(0.5 * (lev[:-1] + lev[1:]))
+    u = [rng.uniform(-1.0, 1.0, us) for _ in range(3)]; v = [rng.uniform(-1.0, 1.0, us) for _ in range(3)]
+    w = [rng.uniform(-1e-3, 1e-3, ws) for _ in range(3)]
+    bed = max(a[0] for a in wz); low = max(a[0] for a in z); top = min(a[-1] for a in wz)
+    if where == 0:
+        Zpar = float(rng.uniform(min(a[0] for a in wz), bed + z0))                 # within z0 of the bed
+    elif where == 1:
+        Zpar = float(rng.uniform(bed + z0, low))                                  # log layer
+    elif where == 2:
+        Zpar = float(rng.uniform(low, top))                                       # interior
+    else:
+        k = int(rng.integers(0, us)); t = int(rng.integers(0, 3)); Zpar = float(z[t][k])      # exactly on a level
+    P = [min(Zpar, float(wz[t][-1]) - 1e-3) for t in range(3)]                     # the clamped depths of LTRANS.f90:905-912
+    ex = np.array([0.0, 3600.0, 7200.0]) + 3600.0 * (p - 1)
+    it = int(rng.integers(0, 28)); ix = (ex[1] if p > 1 else ex[0]) + 120.0 * np.array([it, it + 1.0, it + 2.0])
+    out = np.zeros(3); nf = C.c_int32(0)
+    L.ora_find_currents_column(us, ws, z0, Zpar, dptr(arr(np.concatenate(z))), dptr(arr(np.concatenate(wz))),
+                               dptr(arr(np.concatenate(u))), dptr(arr(np.concatenate(v))), dptr(arr(np.concatenate(w))),
+                               P[0], P[1], P[2], dptr(arr(ex)), dptr(arr(ix)), p, version, dptr(out), C.byref(nf))
+    want = NL.find_currents_column(us, ws, z0, Zpar, [list(a) for a in z], [list(a) for a in wz], [list(a) for a in u], [list(a) for a in v],
+                                   [list(a) for a in w], P[0], P[1], P[2], list(ex), list(ix), p, version)
+    assert nf.value == want[3]
+    for k in range(3):
+        assert same(float(out[k]), want[k]), (where, k, float(out[k]), want[k])
