@@ -433,6 +433,171 @@ def wcts_profile(zb, zc, zf, vb, vc, vf, P_zb, P_zc, P_zf, ex, ix, p, v):
     return (b + c * 4 + f) / 6.0, nfall
 
 
+# ------------------------------------------------------------------------ behavior_module.f90
+def behave(prm, state, P_S, words, Zpar, P_zc, P_zetac, P_age, P_depth, P_U, P_V, P_angle, it, daytime):
+    """behavior_module.f90:181-551 for one particle.  prm: namelist values (dt, idt, twistart, twiend, Em, PI,
+    daylength, Kd, thresh, Sgradient, swimfast, swimslow, swimstart, sink, Hswimspeed, Swimdepth, pediage, deadage);
+    state = dict(behave, swim3, timer, Sprev, zprev, bottom) updated in place; words: genrand_int32 values in draw
+    order (genrand_real1 = word / 4294967295, random_module.f90:213-220).  Single-precision literals of the source
+    (0.80, 0.20, 0.1, 0.49, 0.05 ...) enter as the doubles they widen to; `1.5*24.*3600.` and the like are REAL(4)
+    products that happen to be exact.  -> (XBehav, YBehav, ZBehav, bott, words used)"""
+    f32 = _f32
+    k = [0]
+
+    def real1():
+        w = words[k[0]]; k[0] += 1
+        return float(w) / 4294967295.0
+
+    XBehav = YBehav = ZBehav = 0.0
+    bott = False
+    # initBehave :118-131 (per-particle constants are the namelist values in v.2b)
+    pediage, deadage = prm["pediage"], prm["deadage"]
+    swim1 = (prm["swimfast"] - prm["swimslow"]) / (pediage - prm["swimstart"])
+    swim2 = prm["swimfast"] - swim1 * pediage
+    if P_age >= prm["swimstart"]:                                          # :214-215
+        state["swim3"] = swim1 * P_age + swim2
+    if P_age >= pediage:
+        state["swim3"] = prm["swimfast"]
+    if state["behave"] in (4, 5):                                          # :220-229
+        if P_age >= pediage and P_age < deadage:
+            state["behave"] = 2
+        state["timer"] = max(0.0, state["timer"] - float(prm["dt"]))
+    B = state["behave"]
+    swim3 = state["swim3"]
+
+    def updown(switch):
+        """the recurring block: sign by one draw against `switch`, magnitude by a second draw"""
+        negpos = 1.0
+        dev1 = real1()
+        if dev1 > switch:
+            negpos = -1.0
+        devB = real1()
+        return negpos * devB * swim3
+
+    parBehav = 0.0
+    if B == 1:                                                             # :258-282
+        parBehav = updown(f32(0.80)) if P_zc < (P_zetac - 1.0) else updown(0.5)
+    if B == 2 or (B == 5 and state["timer"] > 0.0):                        # :286-311
+        parBehav = updown(f32(0.20)) if P_zc > (P_depth + 1.0) else updown(0.5)
+    if B == 3:                                                             # :314-353
+        dtime = (daytime - math.trunc(daytime)) * 24.0
+        if dtime > prm["twistart"] and dtime < prm["twiend"]:
+            tst = (dtime - prm["twistart"]) * 3600.0
+            sn = math.sin(prm["PI"] * tst / (prm["daylength"] * 3600.0))
+            E0 = prm["Em"] * sn * sn
+        else:
+            E0 = 0.0
+        P_light = E0 * math.exp(prm["Kd"] * P_zc)
+        if P_light < prm["thresh"]:
+            parBehav = updown(0.5)
+        if P_light > prm["thresh"]:
+            parBehav = updown(f32(0.20))
+    if B == 4:                                                             # :356-407
+        if it == 1:
+            state["Sprev"] = P_S; state["zprev"] = P_zc
+        Sslope = 0.0
+        deltaS = state["Sprev"] - P_S
+        deltaz = state["zprev"] - P_zc
+        if it > 1:
+            Sslope = (deltaS / deltaz) if deltaz != 0.0 else (math.copysign(math.inf, deltaS) * math.copysign(1.0, deltaz) if deltaS != 0.0 else math.nan)
+        btest = 0
+        if abs(Sslope) > prm["Sgradient"]:
+            negpos = 1.0
+            dev1 = real1()
+            if dev1 > f32(0.80):
+                negpos = -1.0
+            parBehav = negpos * swim3
+            btest = 1
+        if btest == 0:
+            negpos = 1.0
+            dev1 = real1()
+            if P_age < 1.5 * 24.0 * 3600.0:
+                switch = f32(0.1)
+            elif P_age < 5.0 * 24.0 * 3600.0:
+                switch = f32(0.49)
+            elif P_age < 8.0 * 24.0 * 3600.0:
+                switch = f32(0.50)
+            else:
+                # DBLE(0.517) widens a REAL(4) literal: it is not the double 0.517
+                switchslope = (f32(0.50) - f32(0.517)) / (8.0 * 24.0 * 3600.0 - pediage)
+                switch = switchslope * P_age + f32(0.50) - switchslope * 8.0 * 24.0 * 3600.0
+                if P_zc < P_depth + 1.0:
+                    switch = f32(0.5)
+            if dev1 > (1 - switch):
+                negpos = -1.0
+            devB = real1()
+            parBehav = negpos * devB * swim3
+        state["Sprev"] = P_S; state["zprev"] = P_zc
+    if B == 5 and state["timer"] == 0.0:                                   # :410-463
+        if it == 1:
+            state["Sprev"] = P_S; state["zprev"] = P_zc
+        Sslope = 0.0
+        deltaS = state["Sprev"] - P_S
+        deltaz = state["zprev"] - P_zc
+        if it > 1:
+            Sslope = (deltaS / deltaz) if deltaz != 0.0 else (math.copysign(math.inf, deltaS) * math.copysign(1.0, deltaz) if deltaS != 0.0 else math.nan)
+        btest = 0
+        if abs(Sslope) > prm["Sgradient"]:
+            negpos = 1.0
+            dev1 = real1()
+            btest = 1
+            state["timer"] = 2.0 * 3600.0
+            if dev1 > f32(0.20):
+                negpos = -1.0
+            parBehav = negpos * swim3
+            if P_age < 3.5 * 24.0 * 3600.0:
+                btest = 0
+                state["timer"] = 0.0
+        if btest == 0:
+            negpos = 1.0
+            dev1 = real1()
+            switch = f32(0.495)
+            if P_age < 1.5 * 24.0 * 3600.0:
+                switch = f32(0.9)
+            if P_age > 2.0 * 24.0 * 3600.0 and P_age < 3.5 * 24.0 * 3600.0:
+                switchslope = (f32(0.3) - f32(0.495)) / (2.0 * 24.0 * 3600.0 - 3.5 * 24.0 * 3600.0)
+                switch = switchslope * P_age + f32(0.3) - switchslope * 2.0 * 24.0 * 3600.0
+            if dev1 > switch:
+                negpos = -1.0
+            devB = real1()
+            parBehav = negpos * devB * swim3
+        state["Sprev"] = P_S; state["zprev"] = P_zc
+    if B == 6:                                                             # :466-471
+        parBehav = prm["sink"] if P_age >= prm["swimstart"] else swim3
+    ZBehav = parBehav * prm["idt"]                                         # :491
+    if B == 7:                                                             # :495-548
+        if it == 1:
+            state["Sprev"] = P_S
+        ca, sa = math.cos(P_angle), math.sin(P_angle)
+        X = P_U * ca - P_V * sa
+        Y = P_U * sa + P_V * ca
+        currentspeed = math.sqrt(X * X + Y * Y)
+        if state["bottom"]:
+            if state["Sprev"] < P_S:
+                state["bottom"] = False
+                ZBehav = P_depth + prm["Swimdepth"]
+            else:
+                ZBehav = -9999.0
+        else:
+            if currentspeed > f32(0.05):
+                Hdistance = prm["Hswimspeed"] * prm["idt"]
+                theta = math.atan(Y / X) if X != 0.0 else math.atan(math.copysign(math.inf, Y) if Y != 0.0 else math.nan)
+                if X > 0.0:
+                    XBehav = Hdistance * math.cos(theta); YBehav = Hdistance * math.sin(theta)
+                if X < 0.0:
+                    XBehav = -1.0 * Hdistance * math.cos(theta); YBehav = -1.0 * Hdistance * math.sin(theta)
+                if X == 0 and Y >= 0.0:
+                    XBehav = 0.0; YBehav = Hdistance
+                if X == 0 and Y <= 0.0:
+                    XBehav = 0.0; YBehav = -1.0 * Hdistance
+                ZBehav = P_depth + prm["Swimdepth"]
+            else:
+                ZBehav = -9999.0
+                state["bottom"] = True
+        bott = state["bottom"]
+    return XBehav, YBehav, ZBehav, bott, k[0]
+
+
 # ------------------------------------------------------------------ LTRANS.f90 (find_currents)
 def find_currents_column(us, ws, z0, Zpar, z, wz, u, v, w, P_zb, P_zc, P_zf, ex, ix, p, version):
     """LTRANS.f90:1422-1614 on a bare column.  z[t][k], wz[t][k]: rho- / w-level depths (t = 0, 1, 2 = back, centre,

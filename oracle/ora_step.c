@@ -57,6 +57,8 @@ struct ora_ctx {
     /* events / stop */
     ltgpu_event* ev; int nev, capev; int bad_particle;
     double last_ix3;
+    /* test hooks, NULL / 0 in every run (ora_behave_case): scripted random words, salinity at the particle */
+    const uint32_t* script; int script_pos; const double* script_PS;
 };
 
 typedef struct {            /* module globals set by setEle / setInterp */
@@ -343,6 +345,7 @@ int32_t ora_rotate_hydro(ora_ctx* c)
 static uint32_t draw_word(prng* g, uint32_t block, int word)
 {
     if (g->c->rng_mode == ORA_RNG_MT) return ora_mt_int32();
+    if (g->c->script) return g->c->script[g->c->script_pos++];
     uint32_t ctr[4] = { g->id_lo, g->id_hi, g->step, block };
     uint32_t key[2] = { (uint32_t)g->c->prm.seed, 0u }, out[4];
     ora_philox4x32_10(ctr, key, out);
@@ -897,11 +900,14 @@ static void behave(ora_ctx* c, const elestate* es, prng* g, double Xpar, double 
         c->timer[n] = fmax(0.0, c->timer[n] - (double)P->dt);              /* ledger 15 */
     }
     if (c->P_behave[n] == 4 || (c->P_behave[n] == 5 && c->timer[n] == 0.0) || c->P_behave[n] == 7) {
-        int i;
-        for (i = 3; i <= us - 2; ++i)
-            if (Zpar < Pwc_zb[i - 1] || Zpar < Pwc_zc[i - 1] || Zpar < Pwc_zf[i - 1]) break;
-        int deplvl = i - 2;
-        P_S = WCTS_ITPI(c, es, FLD_SALT, Xpar, Ypar, deplvl, Pwc_zb, Pwc_zc, Pwc_zf, P_zb, P_zc, P_zf, ex, ix, p, 4);
+        if (c->script_PS) P_S = *c->script_PS;
+        else {
+            int i;
+            for (i = 3; i <= us - 2; ++i)
+                if (Zpar < Pwc_zb[i - 1] || Zpar < Pwc_zc[i - 1] || Zpar < Pwc_zf[i - 1]) break;
+            int deplvl = i - 2;
+            P_S = WCTS_ITPI(c, es, FLD_SALT, Xpar, Ypar, deplvl, Pwc_zb, Pwc_zc, Pwc_zf, P_zb, P_zc, P_zf, ex, ix, p, 4);
+        }
     }
     parBehav = 0.0;
     if (c->P_behave[n] == 1) {                                             /* :258-282 */
@@ -1023,6 +1029,28 @@ static void behave(ora_ctx* c, const elestate* es, prng* g, double Xpar, double 
         }
         *bott = c->bottom[n];
     }
+}
+
+/* behave (behavior_module.f90:181-551) for ONE particle with everything it reads handed in (tests/test_oracle_differential.py):
+ * state = {P_behave, P_swim(n,3), timer, P_Sprev, P_zprev, bottom} in and out, P_S the salinity WCTS_ITPI would return,
+ * words = the genrand_int32 values behind the genrand_real1 calls in draw order; out = XBehav, YBehav, ZBehav, bott,
+ * words used.  Runs the step's own routine on a one-particle context. */
+void ora_behave_case(const ltgpu_params* prm, double state[6], double P_S, const uint32_t* words,
+    double Zpar, double P_zc, double P_zetac, double P_age, double P_depth, double P_U, double P_V, double P_angle,
+    int32_t it, double daytime, double out[5])
+{
+    ora_ctx c; memset(&c, 0, sizeof c);
+    c.prm = *prm; c.rng_mode = ORA_RNG_PHILOX; c.script = words; c.script_pos = 0; c.script_PS = &P_S;
+    int32_t beh = (int32_t)state[0]; double swim3 = state[1], timer = state[2], sprev = state[3], zprev = state[4];
+    uint8_t bottom = state[5] != 0.0;
+    c.P_behave = &beh; c.P_swim3 = &swim3; c.timer = &timer; c.P_Sprev = &sprev; c.P_zprev = &zprev; c.bottom = &bottom;
+    prng g; memset(&g, 0, sizeof g); g.c = &c;
+    double ex[3] = {0, 0, 0}, ix[3] = {0, 0, 0};
+    int bott = 0;
+    behave(&c, NULL, &g, 0.0, 0.0, Zpar, NULL, NULL, NULL, P_zc, P_zc, P_zc, P_zetac, P_age, P_depth, P_U, P_V, P_angle, 0, it,
+           ex, ix, daytime, 2, &bott, &out[0], &out[1], &out[2]);
+    out[3] = (double)bott; out[4] = (double)c.script_pos;
+    state[0] = (double)beh; state[1] = swim3; state[2] = timer; state[3] = sprev; state[4] = zprev; state[5] = (double)bottom;
 }
 
 /* ---- boundary_module.f90:1515-1614 mbounds / ibounds ------------------------ */

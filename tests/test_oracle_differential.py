@@ -465,3 +465,51 @@ def test_find_currents_column_bit_equal(seed, us, p, version, where):
     assert nf.value == want[3]
     for k in range(3):
         assert same(float(out[k]), want[k]), (where, k, float(out[k]), want[k])
+
+
+# ---------------------------------------------------------------- behave
+_BEHAVE_KEYS = ("dt", "idt", "twistart", "twiend", "Em", "PI", "daylength", "Kd", "thresh", "Sgradient", "swimfast", "swimslow",
+                "swimstart", "sink", "Hswimspeed", "Swimdepth", "pediage", "deadage")
+
+
+@settings(max_examples=4000, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 7))
+def test_behave_bit_equal(seed, beh):
+    """behavior_module.f90:181-551, all seven types over their age classes, thresholds (single-precision literals),
+    timers, the salinity-gradient cue, light cue and the tidal-stream state machine: outputs, updated state and the
+    NUMBER of random draws agree between the C oracle's behave and the Python restatement"""
+    from ltrans_b200.host.binding import Params
+    rng = np.random.default_rng(seed)
+    day = 86400.0
+    prm = Params.shipped(numpar=1)
+    prm.Behavior = beh
+    prm.swimslow = float(rng.choice([0.0005, 0.001, 0.005])); prm.swimfast = float(rng.choice([0.003, 0.005]))
+    prm.swimstart = float(rng.choice([0.0, 0.5 * day, 2.0 * day])); prm.pediage = float(rng.choice([3.5 * day, 14.0 * day]))
+    prm.deadage = prm.pediage + float(rng.choice([0.75 * day, 7.0 * day]))
+    prm.Sgradient = float(rng.choice([0.05, 1.0])); prm.sink = float(rng.choice([-0.0003, -0.001]))
+    pd_ = {k: getattr(prm, k) for k in _BEHAVE_KEYS}
+    P_depth = -float(rng.uniform(2.0, 60.0)); P_zetac = float(rng.uniform(-0.4, 0.4))
+    where = int(rng.integers(0, 4))
+    P_zc = [P_depth + rng.uniform(0.0, 1.0), P_zetac - rng.uniform(0.0, 1.0), rng.uniform(P_depth, P_zetac), P_depth + 1.0][where]
+    P_zc = float(P_zc)
+    P_age = float(rng.choice([0.2, 1.0, 1.49, 1.5, 1.8, 2.5, 3.4, 3.6, 4.9, 5.5, 7.9, 8.5, 11.0, 15.0, 20.0, 22.0])) * day + float(rng.uniform(0, 600))
+    state = dict(behave=beh, swim3=float(rng.uniform(0.0, 0.005)), timer=float(rng.choice([0.0, 0.0, 120.0, 3600.0, 7200.0])),
+                 Sprev=float(rng.uniform(5.0, 30.0)), zprev=P_zc + float(rng.choice([0.0, 0.2, -0.2, 1e-3])), bottom=bool(rng.integers(0, 2)))
+    P_S = state["Sprev"] + float(rng.choice([0.0, 0.01, -0.01, 0.5, -0.5]))
+    it = int(rng.choice([1, 2, 17]))
+    daytime = float(rng.uniform(0.0, 9.0))
+    P_angle = float(rng.uniform(-0.6, 0.6)); sp = float(rng.choice([0.0, 0.02, 0.049, 0.051, 0.4]))
+    th = float(rng.uniform(0, 2 * math.pi)); P_U, P_V = sp * math.cos(th), sp * math.sin(th)
+    if rng.integers(0, 8) == 0:
+        P_U, P_V, P_angle = 0.0, float(rng.choice([0.3, -0.3])), 0.0            # X == 0 exactly
+    words = rng.integers(0, 2 ** 32, 8, dtype=np.uint64).astype(np.uint32)
+    sa = np.array([state["behave"], state["swim3"], state["timer"], state["Sprev"], state["zprev"], float(state["bottom"])])
+    out = np.zeros(5)
+    L.ora_behave_case(C.cast(C.byref(prm), C.c_void_p), dptr(sa), P_S, words.ctypes.data_as(C.POINTER(C.c_uint32)),
+                      P_zc, P_zc, P_zetac, P_age, P_depth, P_U, P_V, P_angle, it, daytime, dptr(out))
+    st_ = dict(state)
+    X, Y, Z, bott, used = NL.behave(pd_, st_, P_S, [int(w) for w in words], P_zc, P_zc, P_zetac, P_age, P_depth, P_U, P_V, P_angle, it, daytime)
+    assert used == int(out[4]), (used, out[4])
+    assert same(float(out[0]), X) and same(float(out[1]), Y) and same(float(out[2]), Z) and bool(out[3]) == bool(bott), (out, X, Y, Z, bott)
+    assert int(sa[0]) == st_["behave"] and same(float(sa[1]), st_["swim3"]) and same(float(sa[2]), st_["timer"])
+    assert same(float(sa[3]), st_["Sprev"]) and same(float(sa[4]), st_["zprev"]) and bool(sa[5]) == bool(st_["bottom"])
