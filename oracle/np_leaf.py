@@ -970,6 +970,38 @@ def slevel(zeta, depth, sc, cs, hc32, vtransform):
     raise ValueError("Illegal Vtransform number")
 
 
+# ------------------------------------------------------------------ settlement_module.f90 (step)
+def test_settlement_point(hab, R_ele, P_age, settletime, holes_exist, Px, Py):
+    """settlement_module.f90:485-622 (testSettlement, psettle, hsettle) for one point.  hab: the lists createPolySpecs
+    builds, in the layout of the ABI (polys / holes column-major (5 | 6, edges); poly_start 1-based; elepoly / polyhole
+    as CSR over 0-based polygon / hole indices; maxdis per polygon / hole).  -> polygon id, 0 for none"""
+    if not (P_age >= settletime):
+        return 0
+
+    def first_hit(rows, starts, sizes, maxdis, cand, onin):
+        for pi in cand:
+            start, size = int(starts[pi]), int(sizes[pi])
+            cx, cy = rows[1][start - 1], rows[2][start - 1]
+            dis = math.sqrt(_sq(Px - cx) + _sq(Py - cy))
+            if dis > maxdis[pi]:
+                continue
+            e = [(rows[3][start - 1 + j], rows[4][start - 1 + j]) for j in range(size)]
+            if inpoly(Px, Py, e, onin=onin):
+                return int(round(rows[0][start - 1])), pi
+        return 0, -1
+
+    cand = [int(hab["elepoly_idx"][q]) for q in range(int(hab["elepoly_ptr"][R_ele - 1]), int(hab["elepoly_ptr"][R_ele]))]
+    polyin, pidx = first_hit(hab["polys"], hab["poly_start"], hab["poly_size"], hab["poly_maxdis"], cand, None)    # psettle
+    if polyin <= 0:
+        return 0
+    if holes_exist:                                                                                                # hsettle
+        hc = [int(hab["polyhole_idx"][q]) for q in range(int(hab["polyhole_ptr"][pidx]), int(hab["polyhole_ptr"][pidx + 1]))]
+        holein, _ = first_hit(hab["holes"], hab["hole_start"], hab["hole_size"], hab["hole_maxdis"], hc, False)
+        if holein != 0:
+            return 0
+    return polyin
+
+
 # ---------------------------------------------------------------- settlement_module.f90 (set-up)
 def create_poly_specs_literal(r_ele_x, r_ele_y, polys, maxbdis):
     """createPolySpecs' element loop as written (settlement_module.f90:296-402): every element against every

@@ -1234,6 +1234,18 @@ static int testSettlement(ora_ctx* c, double P_age, int n, double Px, double Py)
     return inpoly;
 }
 
+/* testSettlement (settlement_module.f90:485-622) for a bare point in rho element R_ele of a context whose habitat
+ * has been set (tests/test_oracle_differential.py): the polygon id the point settles in, 0 for none */
+int32_t ora_settle_point(ora_ctx* c, int32_t R_ele, double P_age, double Px, double Py)
+{
+    int32_t re = R_ele; uint8_t st = 0;
+    int32_t* keep_r = c->r_ele; uint8_t* keep_s = c->settle;
+    c->r_ele = &re; c->settle = &st;
+    int r = testSettlement(c, P_age, 0, Px, Py);
+    c->r_ele = keep_r; c->settle = keep_s;
+    return r;
+}
+
 /* ---- error handling shared by the four check sites of update_particles ------ */
 /* returns 1 when the reference would STOP */
 static int handle_error(ora_ctx* c, int n, int code, double t, double revertZ)

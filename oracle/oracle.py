@@ -218,6 +218,7 @@ def leaf():
     lib.ora_intersect_reflect.argtypes = [C.c_void_p, d, d, d, d, pd, pd, pd, pd, pi, pi]
     lib.ora_mbounds.restype = i32; lib.ora_mbounds.argtypes = [C.c_void_p, d, d]
     lib.ora_ibounds.restype = i32; lib.ora_ibounds.argtypes = [C.c_void_p, d, d, pd]
+    lib.ora_settle_point.restype = i32; lib.ora_settle_point.argtypes = [C.c_void_p, i32, d, d, d]
     lib.ora_behave_case.restype = None
     lib.ora_behave_case.argtypes = [C.c_void_p, pd, d, C.POINTER(C.c_uint32)] + [d] * 8 + [i32, d, pd]
     lib.ora_find_currents_column.restype = None

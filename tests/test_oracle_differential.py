@@ -513,3 +513,50 @@ def test_behave_bit_equal(seed, beh):
     assert same(float(out[0]), X) and same(float(out[1]), Y) and same(float(out[2]), Z) and bool(out[3]) == bool(bott), (out, X, Y, Z, bott)
     assert int(sa[0]) == st_["behave"] and same(float(sa[1]), st_["swim3"]) and same(float(sa[2]), st_["timer"])
     assert same(float(sa[3]), st_["Sprev"]) and same(float(sa[4]), st_["zprev"]) and bool(sa[5]) == bool(st_["bottom"])
+
+
+# ---------------------------------------------------------------- testSettlement / psettle / hsettle
+def test_settlement_point_equal():
+    """settlement_module.f90:485-622 on the synthetic habitat (polygons with holes): points inside polygons, inside
+    holes, on polygon vertices and edges, just beyond maxbdis, in elements with and without listed polygons, before
+    and after the settlement age"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from common import World, SMALL, make_params
+    from oracle.oracle import Oracle
+    w = World(**SMALL)
+    hab = w.habitat(npoly=8)
+    prm = make_params(w, 10, Behavior=4, settlementon=1, mortality=0, HTurbOn=0, VTurbOn=0)
+    o = Oracle(); o.create(prm)
+    g = w.grid()
+    o.set_grid(g); o.set_habitat(hab)
+    H = {k: (np.asarray(v).tolist() if not np.isscalar(v) else v) for k, v in hab.items()}
+    rex, rey = g["rx"][g["RE"] - 1], g["ry"][g["RE"] - 1]                 # (nE, 4) corner coordinates
+    rng = np.random.default_rng(5)
+    polys = np.asarray(hab["polys"]); holes = np.asarray(hab["holes"])
+    n_in = n_hole = 0
+    pts = []
+    for k in range(len(hab["poly_id"])):                                   # around every polygon and its hole
+        s0, sz = int(hab["poly_start"][k]) - 1, int(hab["poly_size"][k])
+        cx, cy = polys[1, s0], polys[2, s0]
+        R = float(np.hypot(polys[3, s0] - cx, polys[4, s0] - cy))
+        for _ in range(120):
+            r, th = R * rng.uniform(0.0, 1.3), rng.uniform(0, 2 * np.pi)
+            pts.append((cx + r * np.cos(th), cy + r * np.sin(th)))
+        for j in range(sz):                                                # vertices and edge midpoints
+            pts.append((polys[3, s0 + j], polys[4, s0 + j]))
+            pts.append((0.5 * (polys[3, s0 + j] + polys[3, s0 + (j + 1) % sz]), 0.5 * (polys[4, s0 + j] + polys[4, s0 + (j + 1) % sz])))
+    from oracle import np_leaf
+    for (px, py) in pts:
+        # the element that holds the point (scan: test infrastructure) - also try a neighbour to vary the candidate lists
+        inside = [e for e in range(len(rex)) if np_leaf.gridcell(rex[e].tolist(), rey[e].tolist(), float(px), float(py))]
+        if not inside:
+            continue
+        for R_ele in {inside[0] + 1, min(len(rex), inside[0] + 2)}:
+            for age in (prm.pediage - 1.0, prm.pediage, prm.pediage + 3600.0):
+                got = L.ora_settle_point(o.ctx, R_ele, age, float(px), float(py))
+                want = NL.test_settlement_point(H, R_ele, age, prm.pediage, bool(prm.holesExist), float(px), float(py))
+                assert got == want, (px, py, R_ele, age, got, want)
+                n_in += got > 0
+    o.destroy()
+    assert n_in > 200
