@@ -34,3 +34,30 @@ def test_patches_are_current_and_apply(tmp_path):
     mod = open(os.path.join(ROOT, "fortran", "ltgpu_mod.f90")).read()
     for nm in names:
         assert "NAME='%s'" % nm in mod, nm
+
+
+def test_fortran_params_type_mirrors_the_c_struct():
+    """TYPE, BIND(C) :: ltgpu_params of fortran/ltgpu_mod.f90 against struct ltgpu_params of the header: the same
+    fields in the same order with interoperable kinds (a BIND(C) type is laid out like the C struct only then)"""
+    import re
+    h = open(os.path.join(ROOT, "include", "ltrans_b200.h")).read()
+    m = re.search(r"typedef struct ltgpu_params \{(.*?)\} ltgpu_params;", h, re.S) or re.search(r"struct ltgpu_params \{(.*?)\};", h, re.S)
+    body = re.sub(r"//.*", "", re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S))
+    cfields = []
+    for decl in body.split(";"):
+        parts = decl.replace(",", " ").split()
+        if parts:
+            cfields += [(parts[0], nm) for nm in parts[1:]]
+    f = open(os.path.join(ROOT, "fortran", "ltgpu_mod.f90"), encoding="latin-1").read()
+    m = re.search(r"TYPE, BIND\(C\) :: ltgpu_params(.*?)END TYPE", f, re.S | re.I)
+    ffields = []
+    for line in m.group(1).splitlines():
+        line = line.split("!")[0].strip()
+        if "::" in line:
+            typ, names = line.split("::")
+            ffields += [(typ.replace(" ", "").upper(), nm.strip()) for nm in names.split(",")]
+    assert [n.lower() for _, n in cfields] == [n.lower() for _, n in ffields]
+    ok = {"int32_t": {"INTEGER(C_INT)", "INTEGER(C_INT32_T)"}, "int64_t": {"INTEGER(C_INT64_T)", "INTEGER(C_LONG_LONG)"},
+          "double": {"REAL(C_DOUBLE)"}, "float": {"REAL(C_FLOAT)"}}
+    for (ct, cn), (ft, fn) in zip(cfields, ffields):
+        assert ft in ok[ct], (cn, ct, ft)
