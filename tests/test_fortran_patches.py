@@ -61,3 +61,18 @@ def test_fortran_params_type_mirrors_the_c_struct():
           "double": {"REAL(C_DOUBLE)"}, "float": {"REAL(C_FLOAT)"}}
     for (ct, cn), (ft, fn) in zip(cfields, ffields):
         assert ft in ok[ct], (cn, ct, ft)
+
+
+def test_fortran_interfaces_take_as_many_arguments_as_the_c_prototypes():
+    import re
+    h = re.sub(r"//.*", "", re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ltrans_b200.h")).read(), flags=re.S))
+    protos = {}
+    for m in re.finditer(r"\b(ltgpu_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", h, re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    f = re.sub(r"&\s*\n\s*&?", "", open(os.path.join(ROOT, "fortran", "ltgpu_mod.f90"), encoding="latin-1").read())
+    iface = {}
+    for m in re.finditer(r"(?:FUNCTION|SUBROUTINE)\s+(\w+)\s*\(([^)]*)\)\s*(?:RESULT\(\w+\)\s*)?BIND\(C,\s*NAME='(ltgpu_[a-z_0-9]+)'\)", f, re.I):
+        args = m.group(2).strip()
+        iface[m.group(3)] = 0 if not args else len(args.split(","))
+    assert len(protos) == 28 and protos == iface, {k: (protos.get(k), iface.get(k)) for k in set(protos) | set(iface) if protos.get(k) != iface.get(k)}
